@@ -1,0 +1,175 @@
+"""CPU-only: pins the C++ dual-number oracle (oracle/kite_oracle.hpp) to the independent sympy/mpmath
+goldens (tests/golden/golden.json, made by scripts/make_golden.py) and to SURVEY.md Appendix A."""
+import numpy as np
+import pytest
+
+from conftest import assert_close
+from oracle.oracle_py import KITE, KITE_ID, RIGID_BODY, Oracle, params_from_yaml
+
+TOL = 2e-12   # two independent float64-vs-50-digit restatements
+
+
+def test_rhs_and_jacobians(oracle, golden):
+    for name, c in golden["rhs"].items():
+        f = oracle.rhs(c["x"], c["u"])[0]
+        Jx, Ju = oracle.jac(c["x"], c["u"])
+        assert_close(f, c["f"], TOL, what=f"f[{name}]")
+        assert_close(Jx[0], c["Jx"], TOL, what=f"Jx[{name}]")
+        assert_close(Ju[0], c["Ju"], TOL, what=f"Ju[{name}]")
+
+
+def test_jacobian_sparsity_matches_survey(oracle, golden):
+    # 104 + 7 structural non-zeros when the tether arm is zero
+    c = golden["rhs"]["model_test_u"]
+    Jx, Ju = oracle.jac(c["x"], c["u"])
+    assert int((Jx[0] != 0).sum()) == 104
+    assert int((Ju[0] != 0).sum()) == 7
+
+
+def test_rk4_step_and_sensitivities(oracle, golden):
+    for name, c in golden["rk4_step"].items():
+        xn, Phi, Gam = oracle.rk4_sens(c["x"], c["u"], c["h"])
+        assert_close(xn[0], c["xn"], TOL, what=f"xn[{name}]")
+        assert_close(Phi[0], c["Phi"], 1e-11, what=f"Phi[{name}]")
+        assert_close(Gam[0], c["Gamma"], 1e-11, what=f"Gamma[{name}]")
+
+
+def test_config1_rollout(oracle, golden):
+    """BASELINE.json configs[0]: 10 s at 1 ms, open loop."""
+    c = golden["rollout_config1"]
+    xf, traj = oracle.rollout(c["x0"], c["u"], 10000, c["h"], want_traj=True)
+    for k, ref in c["states_after"].items():
+        assert_close(traj[0, int(k)], ref, 1e-11, what=f"state after {k} steps")
+    # survey-time independent value
+    survey = [2.7030845834920783, -0.13244357494175155, 0.90667392034009757, 0.0039031400464208724,
+              -0.76289756833608439, -0.35559584048370014, 2.2435320190344083, -2.6743848407577450,
+              1.3030254843563795, -0.34692557553911291, -0.36780711330237016, 0.39073452318968758,
+              0.76921200252509402]
+    assert_close(xf[0], survey, 1e-11, what="Appendix A rollout")
+
+
+def test_survey_appendix_rhs(oracle):
+    x = [1.5, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0]
+    f = oracle.rhs(x, [0.1, 0, 0])[0]
+    ref = [2.230498149273e+00, 1.946105464361e-02, 9.593304974432e+00, 0, 8.894917655786e-02, 0, 1.5, 0, 0, 0, 0, 0, 0]
+    assert_close(f, ref, 1e-12, what="Appendix A rhs")
+
+
+def test_ekf_predict(oracle, golden):
+    c = golden["ekf_predict"]
+    xn, Pn = oracle.ekf_predict(c["x"], c["u"], c["dt"], np.array(c["P"])[None], c["W"])
+    assert_close(xn[0], c["xn"], TOL, what="ekf xn")
+    assert_close(Pn[0], c["Pn"], 1e-11, what="ekf Pn")
+    assert abs(np.trace(Pn[0]) - 15.45098842411765) < 1e-11
+    W, V = oracle.ekf_defaults()
+    assert_close(W, c["W"], 1e-15, what="default W")
+
+
+def test_ekf_update_is_kalman(oracle, golden):
+    """Update step (kiteEKF.cpp:108-126) against a numpy restatement."""
+    c = golden["ekf_predict"]
+    W, V = oracle.ekf_defaults()
+    x = np.array(c["xn"]); P = np.array(c["Pn"])
+    z = np.array([1.4522, -3.1274, -1.7034, -0.5455, -0.2382, -0.2922, -0.7485])   # kite_control_test.cpp:51
+    H = np.hstack([np.zeros((7, 6)), np.eye(7)])
+    K = P @ H.T @ np.linalg.inv(H @ P @ H.T + V)
+    x_ref = x + K @ (z - H @ x)
+    P_ref = (np.eye(13) - K @ H) @ P
+    xo, Po = oracle.ekf_update(z, V, x, P[None])
+    assert_close(xo[0], x_ref, 1e-10, what="ekf update x")
+    assert_close(Po[0], P_ref, 1e-9, scale=1e-3, what="ekf update P")
+
+
+@pytest.mark.parametrize("case", ["colloc_generics_P10_S1", "colloc_nmpc_P5_S2_scaled"])
+def test_collocation(oracle, golden, case):
+    c = golden[case]
+    G, JX, JU = oracle.colloc_eval(c["z"], c["P"], c["S"], c["t0"], c["tf"], c["sx"], c["su"])
+    assert_close(G[0], c["G"], 1e-11, what="G")
+    assert_close(JX[0], c["JX"], 1e-11, what="JX")
+    assert_close(JU[0], c["JU"], 1e-11, what="JU")
+
+
+def test_chebyshev_operators(oracle, golden):
+    for name, c in golden["cheb"].items():
+        P, S = c["P"], c["S"]
+        assert_close(oracle.cheb_points(P), c["points"], 1e-14, what="points")
+        assert_close(oracle.cheb_diff(P), c["D"], 1e-13, what="D")
+        assert_close(oracle.cheb_weights(P), c["weights"], 1e-14, what="weights")
+        assert_close(oracle.cheb_compdiff(P, S), c["compD"], 1e-13, what="compD")
+        # closed forms: D00 = (2P^2+1)/6, Clenshaw-Curtis weights sum to 2
+        assert abs(oracle.cheb_diff(P)[0, 0] - (2 * P * P + 1) / 6.0) < 1e-12
+        assert abs(oracle.cheb_weights(P).sum() - 2.0) < 1e-14
+
+
+def test_compdiff_differentiates_quadratic(oracle):
+    P, S, tf = 5, 2, 1.0
+    C = oracle.cheb_compdiff(P, S)
+    tau = tf / (2 * S)
+    xs = oracle.cheb_points(P)
+    # node times, node 0 = final time
+    t = np.concatenate([(xs[:-1] + 1) * tau + tau * 2 * (S - 1 - s) for s in range(S)] + [[0.0]])
+    assert np.abs(C @ t ** 2 - tau * 2 * t).max() < 5e-15
+
+
+def test_tether_arm(yaml_path, golden):
+    c = golden["tether_arm"]
+    prm = params_from_yaml(yaml_path)
+    prm[36:39] = c["tether_arm"]
+    o = Oracle(prm)
+    assert_close(o.rhs(c["x"], c["u"])[0], c["f"], TOL, what="f arm")
+    Jx, Ju = o.jac(c["x"], c["u"])
+    assert_close(Jx[0], c["Jx"], TOL, what="Jx arm")
+    assert int((Jx[0] != 0).sum()) == 104 + 21
+    xn, Phi, Gam = o.rk4_sens(c["x"], c["u"], c["h"])
+    assert_close(Phi[0], c["Phi"], 1e-11, what="Phi arm")
+
+
+def test_identification_variant(oracle, golden):
+    for name, c in golden["rhs_id"].items():
+        f = oracle.rhs(c["x"], c["u"], p=c["p"], kind=KITE_ID)[0]
+        Jx, Ju = oracle.jac(c["x"], c["u"], p=c["p"], kind=KITE_ID)
+        assert_close(f, c["f"], TOL, what=f"id f[{name}]")
+        assert_close(Jx[0], c["Jx"], TOL, what=f"id Jx[{name}]")
+        xf = oracle.rollout(c["x"], c["u"], 1, c["h"], p=c["p"], kind=KITE_ID)
+        assert_close(xf[0], c["xn"], TOL, what=f"id xn[{name}]")
+
+
+def test_rigid_body(oracle, golden):
+    c = golden["rigid_body"]
+    f = oracle.rhs(c["x"], c["u"], kind=RIGID_BODY)[0]
+    assert_close(f, c["f"], TOL, what="rb f")
+    Jx, _ = oracle.jac(c["x"], c["u"], kind=RIGID_BODY)
+    assert_close(Jx[0], c["Jx"], TOL, what="rb Jx")
+    xn, Phi, _ = oracle.rk4_sens(c["x"], c["u"], c["h"], kind=RIGID_BODY)
+    assert_close(xn[0], c["xn"], TOL, what="rb xn")
+    assert_close(Phi[0], c["Phi"], 1e-11, what="rb Phi")
+
+
+def test_invariants(oracle):
+    """Closed-form checks that need no oracle."""
+    rng = np.random.default_rng(0)
+    x = oracle.synth_x0(0, 64)
+    u = rng.uniform(-0.1, 0.1, (64, 3))
+    f = oracle.rhs(x, u)
+    q = x[:, 9:13]
+    assert np.abs((f[:, 9:13] * q).sum(1)).max() < 1e-14            # qdot . q = 0 on the unit sphere
+    # lateral symmetry: v1 = w0 = w2 = dR = 0 and q a pure pitch rotation keep lateral components zero
+    xs = np.array([5.0, 0, 0.4, 0, 0.3, 0, 1.0, 0, -2.5, np.cos(0.2), 0, np.sin(0.2), 0])
+    fs = oracle.rhs(xs, [0.1, 0.02, 0.0])[0]
+    assert abs(fs[1]) < 1e-14 and abs(fs[3]) < 1e-13 and abs(fs[5]) < 1e-13 and abs(fs[7]) < 1e-14
+
+
+def test_flop_counts_near_survey(oracle):
+    fc = oracle.flop_counts()
+    assert abs(fc["rhs"]["flops"] - 435) / 435 < 0.10          # SURVEY.md 8d figure
+    assert abs(fc["rk4_step"]["flops"] - 1909) / 1909 < 0.10
+    assert fc["rhs"]["special"] == 9
+
+
+def test_counter_rng_is_sharding_invariant(oracle):
+    a = oracle.synth_controls(0, 8, 5)
+    b = oracle.synth_controls(4, 4, 5)
+    assert np.array_equal(a[4:], b)
+    assert a[..., 0].min() >= 0 and a[..., 0].max() <= 0.3
+    x0 = oracle.synth_x0(0, 16)
+    assert np.abs(np.linalg.norm(x0[:, 9:13], axis=1) - 1).max() < 1e-15
