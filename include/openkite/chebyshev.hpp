@@ -1,0 +1,143 @@
+// chebyshev.hpp -- host mirror of openKITE's Chebyshev<BaseClass,PolyOrder,NumSegments,NX,NU,NP> collocation
+// class (reference: src/kite_math/pseudospectral/chebyshev.hpp:6-271) for the numeric (DM) use the NMPC makes of it.
+// The one-time operators (points, D, Clenshaw-Curtis weights, composite D) are built on the host exactly as the
+// reference builds them; the per-iteration work -- G(X,U) = (CompD (x) I) X - tau F(X,U) and its Jacobian
+// (kiteNMPF.cpp:94-111,169-171) -- is evaluated by the CUDA kernel k_colloc_eval through kite_colloc_eval.
+#pragma once
+#include <cmath>
+
+#include "kite.hpp"
+
+namespace openkite {
+
+template <int PolyOrder, int NumSegments, int NX, int NU, int NP>
+class Chebyshev {
+public:
+    static constexpr int NODES = NumSegments * PolyOrder + 1;
+
+    Chebyshev() {
+        _Points = CollocPoints();
+        _D = DiffMatrix();
+        _QuadWeights = QuadWeights();
+        _CompDiff = CompDiffBlock();
+    }
+    virtual ~Chebyshev() {}
+
+    DM D() { return _D; }
+    /** composite differentiation matrix kron(CompDiff, I_NX) as the reference returns it (chebyshev.hpp:231) */
+    DM CompD() {
+        DM K(NODES * NX, NODES * NX);
+        for (int i = 0; i < NODES; ++i) for (int j = 0; j < NODES; ++j) { double v = _CompDiff(i, j); if (v != 0.0) for (int k = 0; k < NX; ++k) K(i * NX + k, j * NX + k) = v; }
+        return K;
+    }
+    /** the (S*P+1)^2 block matrix before the Kronecker product (what the engine consumes) */
+    DM CompDBlock() { return _CompDiff; }
+    DM CPoints() { return _Points; }
+    DM QWeights() { return _QuadWeights; }
+
+    /** Collocated dynamics of the scaled augmented kite model (kiteNMPF.cpp:58-111): the returned object evaluates
+     *  G(z) and d G / d z for z = [X (NODES*15) ; U (NODES*4)].  Requires NX = 15, NU = 4. */
+    class Collocated {
+    public:
+        Collocated(std::shared_ptr<KiteContext> ctx, const DM& compd, double tau, const DM& Sx, const DM& Su)
+            : Ctx(ctx), compD_rm(compd.row_major()), tau_(tau), compd_(compd) {
+            for (int i = 0; i < 15; ++i) sx[i] = Sx.size2() > 1 ? Sx(i, i) : Sx[i];
+            for (int i = 0; i < 4; ++i) su[i] = Su.size2() > 1 ? Su(i, i) : Su[i];
+            const size_t nd = (size_t)NODES * (19 + 15 + 225 + 60) + 1;
+            if (kite_device_malloc((void**)&buf, sizeof(double) * nd) != 0) throw std::runtime_error("Collocated: device allocation failed");
+        }
+        ~Collocated() { if (buf) kite_device_free(buf); }
+        Collocated(const Collocated&) = delete;
+
+        /** constraint residual G (NODES*15), as DynamicConstraints / nlp_g (kiteNMPF.cpp:151) */
+        DM G(const DM& z) { DM g, j; eval(z, g, j, false); return g; }
+        /** dense d G / d z (NODES*15 x NODES*19), as AugJacobian (kiteNMPF.cpp:169-171) */
+        DM Jacobian(const DM& z) { DM g, j; eval(z, g, j, true); return j; }
+        void eval(const DM& z, DM& Gout, DM& Jout, bool want_jac = true) {
+            const int M = NODES;
+            if (z.numel() != M * 19) throw std::invalid_argument("Collocated::eval: z must have NODES*(15+4) elements");
+            double* z_d = buf; double* G_d = z_d + M * 19; double* JX_d = G_d + M * 15; double* JU_d = JX_d + M * 225; double* gn_d = JU_d + M * 60;
+            Ctx->h2d(z_d, z.ptr(), (size_t)M * 19);
+            Ctx->check(kite_colloc_eval(Ctx->ctx, 1, 1, M, compD_rm.data(), tau_, sx, su, z_d, nullptr, G_d, want_jac ? JX_d : nullptr,
+                                        want_jac ? JU_d : nullptr, gn_d), "kite_colloc_eval");
+            Gout = DM(M * 15, 1);
+            Ctx->d2h(Gout.ptr(), G_d, (size_t)M * 15);
+            if (!want_jac) return;
+            std::vector<double> jx((size_t)M * 225), ju((size_t)M * 60);
+            Ctx->d2h(jx.data(), JX_d, jx.size()); Ctx->d2h(ju.data(), JU_d, ju.size());
+            // assemble: [kron(CompD, I15) - tau blkdiag(JX_k) | -tau blkdiag(JU_k)]
+            Jout = DM(M * 15, M * 19);
+            for (int k = 0; k < M; ++k) {
+                for (int l = 0; l < M; ++l) { double v = compd_(k, l); if (v != 0.0) for (int i = 0; i < 15; ++i) Jout(k * 15 + i, l * 15 + i) = v; }
+                for (int i = 0; i < 15; ++i) {
+                    for (int j = 0; j < 15; ++j) Jout(k * 15 + i, k * 15 + j) -= tau_ * jx[(size_t)k * 225 + i * 15 + j];
+                    for (int j = 0; j < 4; ++j) Jout(k * 15 + i, M * 15 + k * 4 + j) = -tau_ * ju[(size_t)k * 60 + i * 4 + j];
+                }
+            }
+        }
+        /** batched device entry point (config 4): see kite_colloc_eval in include/kite_b200.h */
+        void eval_device(long B, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d, double* gnorm_d) {
+            Ctx->check(kite_colloc_eval(Ctx->ctx, B, B, NODES, compD_rm.data(), tau_, sx, su, z_d, p_d, G_d, JX_d, JU_d, gnorm_d), "kite_colloc_eval");
+        }
+        double tau() const { return tau_; }
+
+    private:
+        std::shared_ptr<KiteContext> Ctx;
+        std::vector<double> compD_rm;
+        double tau_;
+        DM compd_;
+        double sx[15], su[4];
+        double* buf = nullptr;
+    };
+
+    /** chebyshev.hpp:241-271 with the scaled augmented kite ODE of kiteNMPF.cpp:100-107 as `dynamics`. */
+    std::shared_ptr<Collocated> CollocateDynamics(KiteDynamics& kite, const DM& ScaleX, const DM& ScaleU, const double& t0, const double& tf) {
+        static_assert(NX == 15 && NU == 4 && NP == 0, "the GPU collocation evaluator implements the NMPC's augmented kite model (15 states, 4 controls)");
+        const double t_scale = (tf - t0) / (2 * NumSegments);
+        return std::make_shared<Collocated>(kite.context(), _CompDiff, t_scale, ScaleX, ScaleU);
+    }
+
+private:
+    /** Chebyshev-Gauss-Lobatto points x_k = cos(k pi / P) (chebyshev.hpp:119-127); index 0 is the FINAL time. */
+    static DM CollocPoints() { DM X(PolyOrder + 1, 1); for (int k = 0; k <= PolyOrder; ++k) X[k] = std::cos(k * (M_PI / PolyOrder)); return X; }
+    /** Trefethen's differentiation matrix with the negative-sum diagonal (chebyshev.hpp:136-153). */
+    static DM DiffMatrix() {
+        const int n = PolyOrder + 1;
+        DM x = CollocPoints(), c(n, 1), Dn(n, n), Dm(n, n);
+        for (int k = 0; k < n; ++k) c[k] = ((k % 2) ? -1.0 : 1.0) * ((k == 0 || k == PolyOrder) ? 2.0 : 1.0);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Dn(i, j) = (c[i] * (1.0 / c[j])) / ((x[i] - x[j]) + (i == j ? 1.0 : 0.0));
+        for (int i = 0; i < n; ++i) { double rs = 0; for (int j = 0; j < n; ++j) rs += Dn(i, j); for (int j = 0; j < n; ++j) Dm(i, j) = Dn(i, j) - (i == j ? rs : 0.0); }
+        return Dm;
+    }
+    /** Clenshaw-Curtis weights (chebyshev.hpp:162-195), returned as a 1 x (P+1) row like the reference. */
+    static DM QuadWeights() {
+        const int P = PolyOrder;
+        DM w(1, P + 1);
+        std::vector<double> v(P - 1, 1.0), theta(P + 1);
+        for (int k = 0; k <= P; ++k) theta[k] = k * (M_PI / P);
+        if (P % 2 == 0) {
+            w(0, 0) = 1.0 / (double(P) * P - 1); w(0, P) = w(0, 0);
+            for (int k = 1; k <= P / 2 - 1; ++k) for (int i = 1; i < P; ++i) v[i - 1] -= 2 * std::cos(2 * k * theta[i]) / (4.0 * k * k - 1);
+            for (int i = 1; i < P; ++i) v[i - 1] -= std::cos(P * theta[i]) / (double(P) * P - 1);
+        } else {
+            w(0, 0) = 1.0 / (double(P) * P); w(0, P) = w(0, 0);
+            for (int k = 1; k <= (P - 1) / 2; ++k) for (int i = 1; i < P; ++i) v[i - 1] -= 2 * std::cos(2 * k * theta[i]) / (4.0 * k * k - 1);
+        }
+        for (int i = 1; i < P; ++i) w(0, i) = 2 * v[i - 1] / P;
+        return w;
+    }
+    /** composite block matrix (chebyshev.hpp:204-229): last segment gets the full D, earlier ones its first P rows */
+    static DM CompDiffBlock() {
+        const int m = NODES, n = PolyOrder + 1;
+        DM Dm = DiffMatrix();
+        if (NumSegments < 2) return Dm;
+        DM C(m, m);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) C(m - n + i, m - n + j) = Dm(i, j);
+        for (int k = 0; k < (NumSegments - 1) * PolyOrder; k += PolyOrder)
+            for (int i = 0; i < PolyOrder; ++i) for (int j = 0; j < n; ++j) C(k + i, k + j) = Dm(i, j);
+        return C;
+    }
+    DM _D, _CompDiff, _Points, _QuadWeights;
+};
+
+}  // namespace openkite

@@ -1,0 +1,483 @@
+// =====================================================================================
+// kite_capi.cu -- extern "C" layer of libkite_b200.so (declared in include/kite_b200.h).
+// Thin: argument checks, template dispatch, launches on the context's stream.  No CPU
+// fallback anywhere: every entry point ends in a kernel launch or an error code.
+// =====================================================================================
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kite_consts.h"
+#include "kite_launch.h"
+
+using namespace kite;
+
+// ---- minimal NCCL surface, resolved at run time (no link-time dependency) -------------------------
+typedef struct { char internal[128]; } nccl_unique_id_t;
+typedef void* nccl_comm_t;
+typedef int (*pfn_ncclGetUniqueId)(nccl_unique_id_t*);
+typedef int (*pfn_ncclCommInitRank)(nccl_comm_t*, int, nccl_unique_id_t, int);
+typedef int (*pfn_ncclAllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
+typedef int (*pfn_ncclCommDestroy)(nccl_comm_t);
+typedef const char* (*pfn_ncclGetErrorString)(int);
+struct NcclApi {
+    void* handle = nullptr;
+    pfn_ncclGetUniqueId GetUniqueId = nullptr;
+    pfn_ncclCommInitRank CommInitRank = nullptr;
+    pfn_ncclAllGather AllGather = nullptr;
+    pfn_ncclCommDestroy CommDestroy = nullptr;
+    pfn_ncclGetErrorString GetErrorString = nullptr;
+    bool ok() const { return handle && GetUniqueId && CommInitRank && AllGather && CommDestroy; }
+};
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.handle) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // reuse torch's copy if loaded
+    if (!h) for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return api;
+    api.handle = h;
+    api.GetUniqueId = (pfn_ncclGetUniqueId)dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (pfn_ncclCommInitRank)dlsym(h, "ncclCommInitRank");
+    api.AllGather = (pfn_ncclAllGather)dlsym(h, "ncclAllGather");
+    api.CommDestroy = (pfn_ncclCommDestroy)dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (pfn_ncclGetErrorString)dlsym(h, "ncclGetErrorString");
+    return api;
+}
+
+struct DevBuf {
+    void* ptr = nullptr; size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, n);
+        if (e != cudaSuccess) return (int)e;
+        bytes = n; return 0;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct kite_ctx {
+    KiteConsts K;
+    kite_params params;
+    int device = 0;
+    int model_kind = 0;
+    cudaStream_t stream = nullptr;       // compute stream in use
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    std::string err;
+    long long launches = 0;
+    DevBuf small;                        // W / V / compD staging
+    DevBuf scratch;                      // ekf update out-of-place P
+    DevBuf pipe[2];                      // host-pipeline chunk buffers
+    DevBuf shared_u, shared_y;
+    nccl_comm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+static int fail(kite_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+static int cuda_fail(kite_ctx* c, cudaError_t e, const char* where) {
+    return fail(c, KITE_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
+#define LAUNCH_CHECK(name) do { ctx->launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, name); } while (0)
+
+
+extern "C" {
+
+const char* kite_version(void) { return "kite_b200 0.1 (sm_100a)"; }
+
+int kite_create(kite_ctx** out, const kite_params* params, int model_kind, int device) {
+    if (!out || !params) return KITE_ERR_ARG;
+    if (model_kind < 0 || model_kind > 2) return KITE_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return KITE_ERR_CUDA;   // no CPU fallback
+    kite_ctx* ctx = new kite_ctx();
+    ctx->device = device; ctx->model_kind = model_kind; ctx->params = *params;
+    ctx->K = make_consts(*params, model_kind);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return KITE_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return KITE_OK;
+}
+
+int kite_destroy(kite_ctx* ctx) {
+    if (!ctx) return KITE_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
+    ctx->small.release(); ctx->scratch.release(); ctx->pipe[0].release(); ctx->pipe[1].release();
+    ctx->shared_u.release(); ctx->shared_y.release();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return KITE_OK;
+}
+
+int kite_set_stream(kite_ctx* ctx, void* s) {
+    if (!ctx) return KITE_ERR_ARG;
+    ctx->stream = (cudaStream_t)s;      // NULL = the CUDA default stream
+    return KITE_OK;
+}
+int kite_reset_stream(kite_ctx* ctx) {
+    if (!ctx) return KITE_ERR_ARG;
+    ctx->stream = ctx->own_stream;
+    return KITE_OK;
+}
+int kite_device_malloc(void** ptr_out, size_t bytes) {
+    if (!ptr_out) return KITE_ERR_ARG;
+    return cudaMalloc(ptr_out, bytes) == cudaSuccess ? KITE_OK : KITE_ERR_CUDA;
+}
+int kite_device_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? KITE_OK : KITE_ERR_CUDA; }
+int kite_copy_h2d(kite_ctx* ctx, void* dst_d, const void* src_h, size_t bytes) {
+    if (!ctx || !dst_d || !src_h) return fail(ctx, KITE_ERR_ARG, "kite_copy_h2d: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KITE_OK;
+}
+int kite_copy_d2h(kite_ctx* ctx, void* dst_h, const void* src_d, size_t bytes) {
+    if (!ctx || !dst_h || !src_d) return fail(ctx, KITE_ERR_ARG, "kite_copy_d2h: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KITE_OK;
+}
+int kite_synchronize(kite_ctx* ctx) {
+    if (!ctx) return KITE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KITE_OK;
+}
+const char* kite_last_error(const kite_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+long long kite_launch_count(const kite_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- pointwise ----------------------
+static int point_eval(kite_ctx* ctx, long B, long ld, const double* x, const double* u, const double* p, double* f,
+                      double* Jx, double* Ju, bool jac) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || !x || B < 0 || ld < B) return fail(ctx, KITE_ERR_ARG, "point_eval: bad argument");
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
+    if (!rigid && !u) return fail(ctx, KITE_ERR_ARG, "point_eval: u is required for the kite models");
+    if (rigid && p) return fail(ctx, KITE_ERR_STATE, "point_eval: rigid body has no aero parameters");
+    CK(cudaSetDevice(ctx->device));
+    if (jac) {
+        if (Jx) CK(cudaMemsetAsync(Jx, 0, sizeof(double) * 169 * (size_t)ld, ctx->stream));
+        if (Ju) CK(cudaMemsetAsync(Ju, 0, sizeof(double) * 39 * (size_t)ld, ctx->stream));
+    }
+    PointArgs a{ctx->K, B, ld, x, u, p, f, Jx, Ju};
+    launch_point_eval(a, rigid, p != nullptr, jac, ctx->stream);
+    LAUNCH_CHECK("k_point_eval");
+    return KITE_OK;
+}
+
+int kite_rhs_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d, double* f_d) {
+    if (!f_d) return fail(ctx, KITE_ERR_ARG, "kite_rhs_batch: f_d is null");
+    return point_eval(ctx, B, ld, x_d, u_d, p_d, f_d, nullptr, nullptr, false);
+}
+int kite_jac_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d, double* Jx_d,
+                   double* Ju_d) {
+    if (!Jx_d && !Ju_d) return fail(ctx, KITE_ERR_ARG, "kite_jac_batch: both outputs null");
+    return point_eval(ctx, B, ld, x_d, u_d, p_d, nullptr, Jx_d, Ju_d, true);
+}
+
+// ---------------------------------------------------------------- rollout ------------------------
+int kite_rk4_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const double* x0_d, const double* u_d, int u_mode,
+                     const double* p_d, double* xf_d, double* traj_d, long save_every, const double* y_d, double* cost_d,
+                     int32_t* status_d, long index0) {
+    if (ctx && B == 0) return KITE_OK;      // empty batch: nothing to do, pointers may be null
+    if (!ctx || B < 0 || N < 0 || ld < B || !xf_d) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: bad argument");
+    if (u_mode < 0 || u_mode > 3) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: bad u_mode");
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
+    if (u_mode != KITE_U_SYNTH && !x0_d) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: x0_d is null");
+    if (u_mode != KITE_U_SYNTH && !u_d && !rigid) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: u_d is null");
+    if (rigid && (p_d || u_mode == KITE_U_SYNTH)) return fail(ctx, KITE_ERR_STATE, "kite_rk4_rollout: not valid for rigid body");
+    if ((y_d != nullptr) != (cost_d != nullptr)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: y_d and cost_d go together");
+    if (traj_d && save_every <= 0) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: save_every must be > 0");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    RolloutArgs a{ctx->K, B, ld, N, h, x0_d, u_d, p_d, xf_d, traj_d, save_every > 0 ? save_every : 1, y_d, cost_d, status_d, index0};
+    if (rigid && !u_d) { a.u = x0_d; u_mode = 0; }   // controls do not enter the rigid-body RHS; dummy readable pointer
+    if (u_mode <= 1) launch_rollout_01(a, u_mode, rigid, p_d != nullptr, ctx->stream);
+    else launch_rollout_23(a, u_mode, rigid, p_d != nullptr, ctx->stream);
+    LAUNCH_CHECK("k_rk4_rollout");
+    return KITE_OK;
+}
+
+int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, double* x0_d, double* u_d) {
+    if (!ctx || B < 0 || ld < B || N < 0) return fail(ctx, KITE_ERR_ARG, "kite_synth_inputs: bad argument");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    SynthArgs a{B, ld, N, index0, x0_d, u_d};
+    launch_synth_inputs(a, ctx->stream);
+    LAUNCH_CHECK("k_synth_inputs");
+    return KITE_OK;
+}
+
+// Host-pointer rollout: chunk over trajectories, double-buffered H2D / compute / D2H on three streams.
+int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double* x0_h, const double* u_h, int u_mode,
+                          const double* p_h, double* xf_h, const double* y_h, double* cost_h, int32_t* status_h) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || N < 0 || !xf_h) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: bad argument");
+    if (u_mode < 0 || u_mode > 2 || !x0_h) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: bad u_mode / x0");
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
+    if (!u_h && !rigid) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: u_h is null");
+    if ((y_h != nullptr) != (cost_h != nullptr)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: y/cost go together");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->h2d_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    const bool per_step = (u_mode == KITE_U_PER_STEP);
+    const long u_rows = rigid && !u_h ? 0 : (per_step ? 3 * N : (u_mode == KITE_U_CONST ? 3 : 0));
+    // chunk size: ~512 MiB of per-trajectory input per buffer, multiple of 1024 trajectories
+    const double bytes_per_traj = 8.0 * (13 + u_rows + (p_h ? 21 : 0) + 13 + 1) + 4.0;
+    long Bc = (long)(512.0 * 1024 * 1024 / bytes_per_traj);
+    Bc = std::max(1024L, (Bc / 1024) * 1024);
+    if (Bc > B) Bc = B;
+    const long rows_in = 13 + u_rows + (p_h ? 21 : 0);
+    const size_t chunk_bytes = sizeof(double) * (size_t)Bc * (rows_in + 13 + 1) + sizeof(int32_t) * (size_t)Bc;
+    for (int i = 0; i < 2; ++i)
+        if (ctx->pipe[i].reserve(chunk_bytes)) return fail(ctx, KITE_ERR_CUDA, "kite_rk4_rollout_host: cudaMalloc failed");
+    const double* u_shared_d = nullptr; const double* y_d = nullptr;
+    if (u_mode == KITE_U_SHARED && u_h) {
+        if (ctx->shared_u.reserve(sizeof(double) * 3 * (size_t)std::max(N, 1L))) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+        CK(cudaMemcpyAsync(ctx->shared_u.ptr, u_h, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        u_shared_d = (const double*)ctx->shared_u.ptr;
+    }
+    if (y_h) {
+        if (ctx->shared_y.reserve(sizeof(double) * 13 * (size_t)std::max(N, 1L))) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+        CK(cudaMemcpyAsync(ctx->shared_y.ptr, y_h, sizeof(double) * 13 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        y_d = (const double*)ctx->shared_y.ptr;
+    }
+    const long nchunks = (B + Bc - 1) / Bc;
+    const size_t pitch_h = sizeof(double) * (size_t)B;
+    for (long j = 0; j < nchunks; ++j) {
+        const int b = (int)(j & 1);
+        const long off = j * Bc, n = std::min(Bc, B - off);
+        double* base = (double*)ctx->pipe[b].ptr;
+        double* x0_d = base;
+        double* u_d = x0_d + 13 * Bc;
+        double* p_d = u_d + u_rows * Bc;
+        double* xf_d = p_d + (p_h ? 21 : 0) * Bc;
+        double* cost_d = xf_d + 13 * Bc;
+        int32_t* st_d = (int32_t*)(cost_d + Bc);
+        const size_t pitch_d = sizeof(double) * (size_t)Bc, width = sizeof(double) * (size_t)n;
+        if (j >= 2) CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_cmp[b], 0));     // inputs of chunk j-2 consumed
+        CK(cudaMemcpy2DAsync(x0_d, pitch_d, x0_h + off, pitch_h, width, 13, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        if (u_rows) CK(cudaMemcpy2DAsync(u_d, pitch_d, u_h + off, pitch_h, width, (size_t)u_rows, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        if (p_h) CK(cudaMemcpy2DAsync(p_d, pitch_d, p_h + off, pitch_h, width, 21, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CK(cudaEventRecord(ctx->ev_h2d[b], ctx->h2d_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        if (j >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));         // outputs of chunk j-2 drained
+        const double* uk = (u_mode == KITE_U_SHARED) ? u_shared_d : (u_rows ? u_d : nullptr);
+        int rc = kite_rk4_rollout(ctx, n, Bc, N, h, x0_d, uk, u_mode, p_h ? p_d : nullptr, xf_d, nullptr, 0, y_d,
+                                  y_h ? cost_d : nullptr, status_h ? st_d : nullptr, off);
+        if (rc != KITE_OK) return rc;
+        CK(cudaEventRecord(ctx->ev_cmp[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_cmp[b], 0));
+        CK(cudaMemcpy2DAsync(xf_h + off, pitch_h, xf_d, pitch_d, width, 13, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (cost_h) CK(cudaMemcpyAsync(cost_h + off, cost_d, width, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (status_h) CK(cudaMemcpyAsync(status_h + off, st_d, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CK(cudaEventRecord(ctx->ev_d2h[b], ctx->d2h_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KITE_OK;
+}
+
+// ---------------------------------------------------------------- sensitivities -------------------
+size_t kite_rk4_sens_work_bytes(long B) { return B > 0 ? sizeof(double) * 4 * (size_t)JAC_SLOTS * (size_t)B : 0; }
+
+static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, const double* x, const double* u, double* xn,
+                          double* Phi, double* Gamma, void* work) {
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
+    SensArgs a{ctx->K, B, ld, h, x, u, xn, Phi, Gamma, (double*)work};
+    // scratch uses its own leading dimension == B (ldw); kernels index scratch with a.ld, so ld must equal ldw
+    (void)ldw;
+    launch_sens_stage_jac(a, rigid, ctx->stream);
+    LAUNCH_CHECK("k_sens_stage_jac");
+    launch_sens_propagate(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    LAUNCH_CHECK("k_sens_propagate");
+    return KITE_OK;
+}
+
+int kite_rk4_sens_step(kite_ctx* ctx, long B, long ld, double h, const double* x_d, const double* u_d, double* xn_d,
+                       double* Phi_d, double* Gamma_d, void* work_d) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || !x_d || !xn_d || !Phi_d || !Gamma_d || !work_d)
+        return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_step: bad argument");
+    if (ld != B) return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_step: ld must equal B (scratch shares the leading dimension)");
+    if (!u_d && ctx->model_kind != KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_step: u_d is null");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    return sens_step_impl(ctx, B, ld, B, h, x_d, u_d ? u_d : x_d, xn_d, Phi_d, Gamma_d, work_d);
+}
+
+int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const double* x0_d, const double* u_d,
+                          double* xs_d, double* Phi_d, double* Gamma_d, void* work_d) {
+    if (ctx && (B == 0 || N == 0)) return KITE_OK;
+    if (!ctx || B < 0 || N < 0 || ld < B || !x0_d || !u_d || !xs_d || !Phi_d || !Gamma_d || !work_d)
+        return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_rollout: bad argument");
+    if (ld != B) return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_rollout: ld must equal B");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    // The primal recurrence is sequential in k; each step's (Phi_k, Gamma_k) only depends on x_k, so the chain is
+    // N stream-ordered launches of the single-step pair, step k reading the state written by step k-1.
+    for (long k = 0; k < N; ++k) {
+        const double* xk = (k == 0) ? x0_d : xs_d + (size_t)(k - 1) * 13 * ld;
+        int rc = sens_step_impl(ctx, B, ld, B, h, xk, u_d + (size_t)k * 3 * ld, xs_d + (size_t)k * 13 * ld,
+                                Phi_d + (size_t)k * 169 * ld, Gamma_d + (size_t)k * 39 * ld, work_d);
+        if (rc != KITE_OK) return rc;
+    }
+    return KITE_OK;
+}
+
+// ---------------------------------------------------------------- collocation ---------------------
+int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
+                     const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
+                     double* gnorm_d) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || M < 2 || M > 1024 || !compD_h || !sx_h || !su_h || !z_d || !G_d)
+        return fail(ctx, KITE_ERR_ARG, "kite_colloc_eval: bad argument");
+    if (ctx->model_kind == KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_STATE, "kite_colloc_eval: kite models only");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->small.reserve(sizeof(double) * (size_t)M * M + 4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(ctx->small.ptr, compD_h, sizeof(double) * (size_t)M * M, cudaMemcpyHostToDevice, ctx->stream));
+    if (JX_d) CK(cudaMemsetAsync(JX_d, 0, sizeof(double) * (size_t)M * 225 * (size_t)ld, ctx->stream));
+    if (JU_d) CK(cudaMemsetAsync(JU_d, 0, sizeof(double) * (size_t)M * 60 * (size_t)ld, ctx->stream));
+    CollocArgs a{};
+    a.K = ctx->K; a.B = B; a.ld = ld; a.M = M; a.tau = tau;
+    for (int i = 0; i < 15; ++i) { a.sx[i] = sx_h[i]; a.isx[i] = 1.0 / sx_h[i]; }
+    for (int i = 0; i < 4; ++i) { a.su[i] = su_h[i]; a.isu[i] = 1.0 / su_h[i]; }
+    a.compD = (const double*)ctx->small.ptr;
+    a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d;
+    launch_colloc_eval(a, p_d != nullptr, ctx->stream);
+    LAUNCH_CHECK("k_colloc_eval");
+    return KITE_OK;
+}
+
+// ---------------------------------------------------------------- EKF -----------------------------
+size_t kite_ekf_work_bytes(long B) { return B > 0 ? sizeof(double) * (size_t)JAC_SLOTS * (size_t)B : 0; }
+
+int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const double* x_d, const double* u_d,
+                           const double* P_d, const double* W_h, double* xn_d, double* Pn_d, void* work_d) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || !x_d || !P_d || !W_h || !xn_d || !Pn_d || !work_d)
+        return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: bad argument");
+    if (ld != B) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: ld must equal B");
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
+    if (!rigid && !u_d) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: u_d is null");
+    if (P_d == Pn_d) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: P_d and Pn_d must not alias");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(ctx->small.ptr, W_h, sizeof(double) * 169, cudaMemcpyHostToDevice, ctx->stream));
+    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (double*)work_d, (const double*)ctx->small.ptr};
+    launch_ekf_state_jac(a, rigid, ctx->stream);
+    LAUNCH_CHECK("k_ekf_state_jac");
+    launch_ekf_cov(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    LAUNCH_CHECK("k_ekf_cov");
+    return KITE_OK;
+}
+
+int kite_ekf_update_batch(kite_ctx* ctx, long B, long ld, const double* z_d, const double* V_h, double* x_d, double* P_d) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || !z_d || !V_h || !x_d || !P_d) return fail(ctx, KITE_ERR_ARG, "kite_ekf_update_batch: bad argument");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    if (ctx->scratch.reserve(sizeof(double) * 169 * (size_t)ld)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    double* Vd = (double*)ctx->small.ptr + 256;     // keep clear of W staging
+    CK(cudaMemcpyAsync(Vd, V_h, sizeof(double) * 49, cudaMemcpyHostToDevice, ctx->stream));
+    EkfUpdArgs a{B, ld, z_d, P_d, x_d, (double*)ctx->scratch.ptr, Vd};
+    launch_ekf_update(a, ctx->stream);
+    LAUNCH_CHECK("k_ekf_update");
+    CK(cudaMemcpyAsync(P_d, ctx->scratch.ptr, sizeof(double) * 169 * (size_t)ld, cudaMemcpyDeviceToDevice, ctx->stream));
+    return KITE_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU -----------------------
+int kite_comm_unique_id(char id_out[128]) {
+    NcclApi& n = nccl_api();
+    if (!n.ok() || !id_out) return KITE_ERR_NCCL;
+    nccl_unique_id_t id;
+    if (n.GetUniqueId(&id) != 0) return KITE_ERR_NCCL;
+    std::memcpy(id_out, id.internal, 128);
+    return KITE_OK;
+}
+int kite_comm_init(kite_ctx* ctx, int nranks, int rank, const char id[128]) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, KITE_ERR_ARG, "kite_comm_init: bad argument");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(ctx, KITE_ERR_NCCL, "kite_comm_init: libnccl not found");
+    CK(cudaSetDevice(ctx->device));
+    nccl_unique_id_t uid; std::memcpy(uid.internal, id, 128);
+    int rc = n.CommInitRank(&ctx->comm, nranks, uid, rank);
+    if (rc != 0) return fail(ctx, KITE_ERR_NCCL, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+    ctx->nranks = nranks; ctx->rank = rank;
+    return KITE_OK;
+}
+int kite_allgather(kite_ctx* ctx, const double* send_d, double* recv_d, long count) {
+    if (!ctx || !send_d || !recv_d || count < 0) return fail(ctx, KITE_ERR_ARG, "kite_allgather: bad argument");
+    if (!ctx->comm) return fail(ctx, KITE_ERR_STATE, "kite_allgather: communicator not initialised");
+    NcclApi& n = nccl_api();
+    CK(cudaSetDevice(ctx->device));
+    int rc = n.AllGather(send_d, recv_d, (size_t)count, /*ncclFloat64*/ 8, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(ctx, KITE_ERR_NCCL, std::string("ncclAllGather: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+    return KITE_OK;
+}
+int kite_comm_destroy(kite_ctx* ctx) {
+    if (!ctx) return KITE_ERR_ARG;
+    if (ctx->comm && nccl_api().ok()) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    return KITE_OK;
+}
+
+// ---------------------------------------------------------------- diagnostics ---------------------
+int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out) {
+    if (!ctx || iters <= 0 || !tflops_out) return fail(ctx, KITE_ERR_ARG, "kite_fp64_peak: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    if (ctx->scratch.reserve(sizeof(double) * (size_t)blocks * threads)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch_fp64_peak((double*)ctx->scratch.ptr, iters / 8 + 1, blocks, threads, ctx->stream);   // warm-up
+    CK(cudaEventRecord(e0, ctx->stream));
+    launch_fp64_peak((double*)ctx->scratch.ptr, iters, blocks, threads, ctx->stream);
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->launches += 2;
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double flops = 2.0 * (double)FP64_PEAK_FMAS_PER_ITER * iters * (double)blocks * threads;
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    return KITE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// kite_launch.h -- launcher functions, one translation unit per kernel family so nvcc can build them in parallel.
+#pragma once
+#include "kite_kernels.cuh"
+
+namespace kite {
+void launch_point_eval(const PointArgs& a, bool rigid, bool percoef, bool jac, cudaStream_t s);
+void launch_rollout_01(const RolloutArgs& a, int umode, bool rigid, bool percoef, cudaStream_t s);
+void launch_rollout_23(const RolloutArgs& a, int umode, bool rigid, bool percoef, cudaStream_t s);
+void launch_synth_inputs(const SynthArgs& a, cudaStream_t s);
+void launch_sens_stage_jac(const SensArgs& a, bool rigid, cudaStream_t s);
+void launch_sens_propagate(const SensArgs& a, bool rigid, bool arm, cudaStream_t s);
+void launch_ekf_state_jac(const EkfArgs& a, bool rigid, cudaStream_t s);
+void launch_ekf_cov(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
+void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
+void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s);
+void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s);
+inline unsigned blocks_for(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+}  // namespace kite

@@ -1,0 +1,174 @@
+// host_api_test.cpp -- exercises the C++ host mirror (include/openkite/*.hpp) the way the reference's Boost tests
+// exercise the original classes (kite_model_test.cpp: ode_solver_test; kite_control_test.cpp: ekf_test,
+// pseudo_test, full_generics_test), but with assertions: expected values come from tests/golden (written to a flat
+// text file by the pytest wrapper) or from closed forms.  Needs a GPU, except `--cpu-only` (YAML, Dict, Chebyshev).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "openkite/chebyshev.hpp"
+#include "openkite/integrator.hpp"
+#include "openkite/kiteEKF.hpp"
+
+using namespace openkite;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+static bool close_vec(const DM& a, const std::vector<double>& b, double rtol) {
+    if ((size_t)a.numel() != b.size()) return false;
+    for (size_t i = 0; i < b.size(); ++i) if (std::fabs(a[(int)i] - b[i]) > rtol * std::fmax(std::fabs(b[i]), 1.0)) { std::printf("  mismatch at %zu: %.17g vs %.17g\n", i, a[(int)i], b[i]); return false; }
+    return true;
+}
+static std::vector<double> read_vec(std::ifstream& f, const std::string& tag) {
+    std::string t; size_t n;
+    f >> t >> n;
+    if (t != tag) { std::printf("golden file: expected tag %s got %s\n", tag.c_str(), t.c_str()); std::exit(2); }
+    std::vector<double> v(n);
+    for (auto& x : v) f >> x;
+    return v;
+}
+
+static void cpu_only_tests(const std::string& yaml) {
+    // LoadProperties (kite.cpp:7-76) incl. the missing tether arm keys
+    KiteProperties p = kite_utils::LoadProperties(yaml);
+    CHECK(p.Name == "umx_radian");
+    CHECK(p.Geometry.WingSpan == 0.73 && p.Geometry.AerodynamicCenter == 0.25);
+    CHECK(p.Inertia.Ixz == -3.5e-5 && p.Aerodynamics.CDde == -0.0037 && p.Aerodynamics.Cmq == -12.665);
+    CHECK(p.Tether.length == 2.81 && p.Tether.rx == 0.0 && p.Tether.rz == 0.0);
+    bool threw = false;
+    try { kite_utils::LoadProperties("/nonexistent.yaml"); } catch (const std::exception&) { threw = true; }
+    CHECK(threw);
+    // pseudo_test (kite_control_test.cpp:161-217): operators for poly order 2 x 3 segments, and the NMPC's 5 x 2
+    Chebyshev<2, 3, 2, 1, 0> small;
+    CHECK(small.CPoints().numel() == 3 && std::fabs(small.CPoints()[1]) < 1e-16);
+    CHECK(small.CompD().size1() == 7 * 2 && small.CompD().size2() == 7 * 2);
+    Chebyshev<5, 2, 15, 4, 0> nm;
+    CHECK(std::fabs(nm.D()(0, 0) - 8.5) < 1e-13);                  // (2P^2+1)/6
+    CHECK(std::fabs(nm.D()(0, 1) + 10.472135954999580) < 1e-12);
+    double ws = 0; for (int i = 0; i < 6; ++i) ws += nm.QWeights()(0, i);
+    CHECK(std::fabs(ws - 2.0) < 1e-14);
+    DM C = nm.CompDBlock();
+    CHECK(C(0, 6) == 0.0 && C(4, 5) != 0.0 && C(5, 4) == 0.0 && C(10, 5) != 0.0);     // block pattern
+    // composite matrix differentiates t^2 exactly: CompD t^2 = tau 2 t
+    const double tau = 1.0 / 4.0; double worst = 0;
+    std::vector<double> t(11);
+    for (int k = 0; k < 5; ++k) t[k] = (nm.CPoints()[k] + 1) * tau + 2 * tau;
+    for (int k = 0; k < 6; ++k) t[5 + k] = (nm.CPoints()[k] + 1) * tau;
+    for (int i = 0; i < 11; ++i) { double s = 0; for (int j = 0; j < 11; ++j) s += C(i, j) * t[j] * t[j]; worst = std::fmax(worst, std::fabs(s - tau * 2 * t[i])); }
+    CHECK(worst < 5e-15);
+}
+
+int main(int argc, char** argv) {
+    std::string yaml = "data/umx_radian.yaml", gold = "";
+    bool cpu_only = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--cpu-only") cpu_only = true;
+        else if (a == "--yaml") yaml = argv[++i];
+        else if (a == "--golden") gold = argv[++i];
+    }
+    cpu_only_tests(yaml);
+    if (cpu_only) { std::printf("host_api_test (cpu-only): %d failures\n", failures); return failures ? 1 : 0; }
+
+    std::ifstream gf(gold);
+    if (!gf) { std::printf("cannot open golden file %s\n", gold.c_str()); return 2; }
+    KiteProperties kite_props = kite_utils::LoadProperties(yaml);
+    AlgorithmProperties algo_props; algo_props.Integrator = RK4;
+
+    // ---- ode_solver_test (kite_model_test.cpp:12-113) ------------------------------------------------------
+    KiteDynamics kite(kite_props, algo_props);
+    Function ode = kite.getNumericDynamics();
+    CHECK(ode.name() == "dynamics" && ode.nnz_out() == 13 && ode.nnz_in() == 16);
+    Dict opts; opts["tf"] = 5.0; opts["poly_order"] = 41; opts["tol"] = 1e-4; opts["method"] = IntType::RK4;
+    ODESolver rk4_solver(ode, opts);
+    CHECK(rk4_solver.dim_x() == 13 && rk4_solver.dim_u() == 3);
+    CHECK(rk4_solver.getParams()["tf"] == 5.0);
+    DM init_state = DM::vertcat({DM{6.1977743e+00, -2.8407148e-02, 9.1815942e-01, 2.9763089e-01, -2.2052198e+00, -1.4827499e-01},
+                                 DM{-4.1624807e-01, -2.2601052e+00, 1.2903439e+00, 3.5646195e-02, -6.9986094e-02, 8.2660637e-01, 5.5727089e-01}});
+    DM control = DM{0.1, 0.0, 0.0};
+    std::vector<double> f_ref = read_vec(gf, "rhs_model_test");
+    CHECK(close_vec(ode(DMVector{init_state, control})[0], f_ref, 1e-9));
+    std::vector<double> jx_ref = read_vec(gf, "jx_model_test");         // row-major 13x13
+    DM Jx = kite.getNumericJacobian()(DMVector{init_state, control})[0];
+    { bool ok = true; for (int i = 0; i < 13; ++i) for (int j = 0; j < 13; ++j) ok = ok && std::fabs(Jx(i, j) - jx_ref[i * 13 + j]) <= 1e-9 * std::fmax(1.0, std::fabs(jx_ref[i * 13 + j])); CHECK(ok); }
+    // the caller's time loop around solve(): 10 s at 1 ms (BASELINE.json configs[0], simulator.cpp:43-51)
+    std::vector<double> x1_ref = read_vec(gf, "config1_after_1"), x1000_ref = read_vec(gf, "config1_after_1000");
+    DM x = init_state;
+    x = rk4_solver.solve(x, control, 1e-3);
+    CHECK(close_vec(x, x1_ref, 1e-9));
+    for (int k = 1; k < 1000; ++k) x = rk4_solver.solve(x, control, 1e-3);
+    CHECK(close_vec(x, x1000_ref, 1e-9));
+    // the Function "RK4"(X,U,dT) handle gives the same step (kite.cpp:338)
+    Function RK4f = kite.getNumericIntegrator();
+    CHECK(RK4f.name().find("RK4") != std::string::npos);
+    CHECK(close_vec(RK4f(DMVector{init_state, control, DM(1e-3)})[0], x1_ref, 1e-9));
+    // unknown dict key prints a warning and is ignored (integrator.cpp:107); CVODES is out of scope and throws
+    Dict bad; bad["no_such_key"] = 1; rk4_solver.updateParams(bad);
+    CHECK(rk4_solver.getParams().count("no_such_key") == 0);
+    Dict cv; cv["method"] = IntType::CVODES; ODESolver cvs(ode, cv);
+    bool threw = false; try { cvs.solve(init_state, control, 1e-3); } catch (const std::exception&) { threw = true; }
+    CHECK(threw);
+
+    // ---- ekf_test (kite_control_test.cpp:46-86) -------------------------------------------------------------
+    {
+        double dt = 0.0084;
+        DM ctl = DM{0, 0, 0};
+        DM measurement = DM{1.4522, -3.1274, -1.7034, -0.5455, -0.2382, -0.2922, -0.7485};
+        DM x_est = DM::vertcat({DM{6.0026, -0.3965, 0.1705, 0.4414, -0.2068, 0.9293, 1.4634}, DM{-3.1765, -1.7037, -0.5486, -0.2354, -0.2922, -0.7471}});
+        KiteEKF estimator(kite_props, algo_props);
+        estimator.setControl(ctl);
+        estimator.setEstimation(x_est);
+        estimator.propagate(dt);
+        CHECK(close_vec(estimator.getEstimation(), read_vec(gf, "ekf_xn"), 1e-9));
+        std::vector<double> pn = read_vec(gf, "ekf_Pn");
+        DM Pn = estimator.getEstimationCovariance();
+        { bool ok = true; for (int i = 0; i < 13; ++i) for (int j = 0; j < 13; ++j) ok = ok && std::fabs(Pn(i, j) - pn[i * 13 + j]) <= 1e-9 * std::fmax(1.0, std::fabs(pn[i * 13 + j])); CHECK(ok); }
+        // full _estimate = propagate + update; measured components are pulled onto the measurement
+        KiteEKF est2(kite.getNumericIntegrator(), kite.getNumericJacobian());
+        est2.setControl(ctl); est2.setEstimation(x_est);
+        est2._estimate(measurement, dt);
+        DM xe = est2.getEstimation();
+        for (int i = 0; i < 7; ++i) CHECK(std::fabs(xe[6 + i] - measurement[i]) < 2e-3);
+        CHECK(close_vec(xe, read_vec(gf, "ekf_est"), 1e-8));
+        // Q8: an integrator whose name has neither "RK4" nor "CVODES" leaves the state untouched
+        Function odd("mystery", {13, 3, 1}, {13}, [](const DMVector& a) { return DMVector{a[0]}; }, kite.context());
+        KiteEKF est3(odd, kite.getNumericJacobian());
+        est3.setEstimation(x_est); est3.propagate(dt);
+        CHECK(close_vec(est3.getEstimation(), x_est.nonzeros(), 0.0));
+    }
+
+    // ---- rigid body (kite_control_test.cpp:12-44) --------------------------------------------------------
+    {
+        RigidBodyKinematics rb(algo_props);
+        DM s0 = DM::vertcat({DM{4.318732, 0.182552, 0.254833, 1.85435, -0.142882, -0.168359}, DM{-0.229383, -0.0500282, -0.746832, 0.189409, -0.836349, -0.48178, 0.180367}});
+        CHECK(close_vec(rb.getNumericDynamcis()(DMVector{s0})[0], read_vec(gf, "rb_f"), 1e-9));
+        CHECK(close_vec(rb.getNumericIntegrator()(DMVector{s0, DM::zeros(3), DM(0.02)})[0], read_vec(gf, "rb_xn"), 1e-9));
+    }
+
+    // ---- full_generics_test-style collocation (kite_control_test.cpp:444-605), NMPC config (P=5,S=2, scaled) ----
+    {
+        std::vector<double> sx = read_vec(gf, "colloc_sx"), su = read_vec(gf, "colloc_su"), z = read_vec(gf, "colloc_z");
+        std::vector<double> Gref = read_vec(gf, "colloc_G"), Jref = read_vec(gf, "colloc_J");   // J dense 165x209 row-major
+        Chebyshev<5, 2, 15, 4, 0> spectral;
+        auto coll = spectral.CollocateDynamics(kite, DM::diag(DM(sx)), DM::diag(DM(su)), 0.0, 1.0);
+        DM G, J;
+        coll->eval(DM(z), G, J);
+        CHECK(close_vec(G, Gref, 1e-9));
+        bool ok = J.size1() == 165 && J.size2() == 209;
+        for (int i = 0; ok && i < 165; ++i) for (int j = 0; j < 209; ++j) if (std::fabs(J(i, j) - Jref[(size_t)i * 209 + j]) > 1e-9 * std::fmax(1.0, std::fabs(Jref[(size_t)i * 209 + j]))) { ok = false; std::printf("  J mismatch %d %d\n", i, j); break; }
+        CHECK(ok);
+    }
+
+    // ---- identification variant (kite.cpp:365-616): dynamics(x,u,p) ------------------------------------------
+    {
+        KiteDynamics kid(kite_props, algo_props, true);
+        std::vector<double> p = read_vec(gf, "id_p");
+        CHECK(kid.getNumericDynamics().n_in() == 3);
+        CHECK(kid.getNumericIntegrator().is_null());
+        CHECK(close_vec(kid.getNumericDynamics()(DMVector{init_state, DM{0.25, -0.11, 0.09}, DM(p)})[0], read_vec(gf, "id_f"), 1e-9));
+    }
+    std::printf("host_api_test: %d failures\n", failures);
+    return failures ? 1 : 0;
+}

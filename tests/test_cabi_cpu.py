@@ -1,0 +1,71 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every symbol that
+include/kite_b200.h declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from openkite_b200 import build
+    build.build()
+    import openkite_b200 as okb
+    return okb.load_library()
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "kite_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kite_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for s in ("kite_create", "kite_destroy", "kite_rhs_batch", "kite_jac_batch", "kite_rk4_rollout", "kite_rk4_rollout_host",
+              "kite_rk4_sens_step", "kite_rk4_sens_rollout", "kite_colloc_eval", "kite_ekf_predict_batch",
+              "kite_ekf_update_batch", "kite_allgather", "kite_comm_init", "kite_fp64_peak"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), "libkite_b200.so does not export %s" % s
+
+
+def test_params_struct_matches_header():
+    import openkite_b200 as okb
+    txt = open(os.path.join(ROOT, "include", "kite_b200.h")).read()
+    body = re.search(r"typedef struct kite_params \{(.*?)\} kite_params;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for n in re.findall(r"([A-Za-z_0-9]+)\s*[,;]", body.replace("double", ""))]
+    assert names == okb.engine.PARAM_FIELDS
+    assert C.sizeof(okb.KiteParams) == 39 * 8
+
+
+def test_load_properties_defaults_missing_tether_arm(yaml_path):
+    import openkite_b200 as okb
+    p = okb.load_properties(yaml_path)
+    assert (p.rx, p.ry, p.rz) == (0.0, 0.0, 0.0)
+    assert p.b == 0.73 and p.mass == 0.044 and p.tether_length == 2.81 and p.CLa_total == 4.483
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback(lib, yaml_path):
+    import openkite_b200 as okb
+    p = okb.load_properties(yaml_path)
+    ctx = C.c_void_p()
+    assert lib.kite_create(C.byref(ctx), C.byref(p), 0, 0) == -2      # KITE_ERR_CUDA
+    assert not ctx.value
+    with pytest.raises(okb.KiteError):
+        okb.Engine(p)
+
+
+def test_work_size_queries(lib):
+    assert lib.kite_rk4_sens_work_bytes(10) == 8 * 4 * 132 * 10
+    assert lib.kite_ekf_work_bytes(10) == 8 * 132 * 10
+    assert lib.kite_rk4_sens_work_bytes(0) == 0

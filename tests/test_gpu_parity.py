@@ -1,0 +1,316 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against
+  (a) the committed sympy/mpmath golden vectors (tests/golden/golden.json) and
+  (b) the C++ oracle on seeded inputs.
+Tolerance (BASELINE.json north_star): |gpu - ref| <= 1e-9 * max(|ref|, 1) on final states and Jacobian entries.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def okb():
+    import openkite_b200 as okb
+    return okb
+
+
+@pytest.fixture(scope="module")
+def params(okb, yaml_path):
+    return okb.load_properties(yaml_path)
+
+
+@pytest.fixture(scope="module")
+def eng(okb, params):
+    return okb.Engine(params, okb.KITE)
+
+
+def soa(a):
+    """[B, n...] numpy AoS -> [n, B] CUDA SoA"""
+    a = np.asarray(a, dtype=np.float64)
+    a = a.reshape(a.shape[0], -1)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+
+
+def aos(t, *shape):
+    a = t.detach().cpu().numpy().T
+    return a.reshape(a.shape[0], *shape) if shape else a
+
+
+# ---------------------------------------------------------------- golden vectors ------------------
+def test_library_loaded_is_in_tree(okb):
+    import os
+    assert os.path.exists(okb.LIB_PATH) and okb.LIB_PATH.endswith("openkite_b200/libkite_b200.so")
+    assert b"sm_100a" in okb.load_library().kite_version()
+
+
+def test_rhs_jac_golden(eng, golden):
+    names = list(golden["rhs"])
+    x = soa([golden["rhs"][n]["x"] for n in names]); u = soa([golden["rhs"][n]["u"] for n in names])
+    f = aos(eng.rhs(x, u)); Jx, Ju = eng.jac(x, u)
+    Jx = aos(Jx, 13, 13); Ju = aos(Ju, 13, 3)
+    for i, n in enumerate(names):
+        c = golden["rhs"][n]
+        assert_close(f[i], c["f"], RTOL, what=f"f[{n}]")
+        assert_close(Jx[i], c["Jx"], RTOL, what=f"Jx[{n}]")
+        assert_close(Ju[i], c["Ju"], RTOL, what=f"Ju[{n}]")
+
+
+def test_config1_rollout_golden(eng, golden, okb):
+    """BASELINE.json configs[0]: umx_radian, 10 s at dt = 1 ms, one trajectory (B = 1 semantics)."""
+    c = golden["rollout_config1"]
+    x0 = soa([c["x0"]]); u = soa([c["u"]])
+    out = eng.rollout(x0, u, 10000, c["h"], okb.U_CONST, save_every=1000)
+    assert int(out["status"][0]) == 0
+    assert_close(aos(out["xf"])[0], c["states_after"]["10000"], RTOL, what="final state after 10 s")
+    traj = out["traj"].cpu().numpy()[:, :, 0]
+    assert_close(traj[0], c["states_after"]["1000"], RTOL, what="state after 1000 steps")
+    assert_close(traj[4], c["states_after"]["5000"], RTOL, what="state after 5000 steps")
+
+
+def test_rk4_sens_golden(eng, golden):
+    for n, c in golden["rk4_step"].items():
+        xn, Phi, Gam = eng.sens_step(soa([c["x"]]), soa([c["u"]]), c["h"])
+        assert_close(aos(xn)[0], c["xn"], RTOL, what=f"xn[{n}]")
+        assert_close(aos(Phi, 13, 13)[0], c["Phi"], RTOL, what=f"Phi[{n}]")
+        assert_close(aos(Gam, 13, 3)[0], c["Gamma"], RTOL, what=f"Gamma[{n}]")
+
+
+def test_ekf_predict_golden(eng, golden):
+    c = golden["ekf_predict"]
+    xn, Pn = eng.ekf_predict(soa([c["x"]]), soa([c["u"]]), c["dt"], soa([np.array(c["P"]).ravel()]), c["W"])
+    assert_close(aos(xn)[0], c["xn"], RTOL, what="ekf xn")
+    assert_close(aos(Pn, 13, 13)[0], c["Pn"], RTOL, what="ekf Pn")
+
+
+@pytest.mark.parametrize("case", ["colloc_generics_P10_S1", "colloc_nmpc_P5_S2_scaled"])
+def test_colloc_golden(eng, golden, oracle, case):
+    c = golden[case]
+    M = c["S"] * c["P"] + 1
+    compD = np.array(golden["cheb"]["P%d_S%d" % (c["P"], c["S"])]["compD"])
+    tau = (c["tf"] - c["t0"]) / (2 * c["S"])
+    G, JX, JU, gn = eng.colloc_eval(soa([c["z"]]), M, compD, tau, c["sx"], c["su"])
+    assert_close(aos(G)[0], c["G"], RTOL, what="G")
+    assert_close(aos(JX, M, 15, 15)[0], c["JX"], RTOL, what="JX")
+    assert_close(aos(JU, M, 15, 4)[0], c["JU"], RTOL, what="JU")
+    assert_close(gn.cpu().numpy()[0], np.sum(np.array(c["G"]) ** 2), 1e-9, what="|G|^2")
+
+
+def test_tether_arm_golden(okb, params, golden):
+    c = golden["tether_arm"]
+    p2 = okb.KiteParams.from_buffer_copy(params)
+    p2.rx, p2.ry, p2.rz = c["tether_arm"]
+    e = okb.Engine(p2, okb.KITE)
+    x, u = soa([c["x"]]), soa([c["u"]])
+    assert_close(aos(e.rhs(x, u))[0], c["f"], RTOL, what="f arm")
+    Jx, Ju = e.jac(x, u)
+    assert_close(aos(Jx, 13, 13)[0], c["Jx"], RTOL, what="Jx arm")
+    xn, Phi, Gam = e.sens_step(x, u, c["h"])
+    assert_close(aos(xn)[0], c["xn"], RTOL, what="xn arm")
+    assert_close(aos(Phi, 13, 13)[0], c["Phi"], RTOL, what="Phi arm")
+    assert_close(aos(Gam, 13, 3)[0], c["Gamma"], RTOL, what="Gamma arm")
+    e.close()
+
+
+def test_identification_variant_golden(okb, params, golden):
+    e = okb.Engine(params, okb.KITE_ID)
+    for n, c in golden["rhs_id"].items():
+        x, u, p = soa([c["x"]]), soa([c["u"]]), soa([c["p"]])
+        assert_close(aos(e.rhs(x, u, p))[0], c["f"], RTOL, what=f"id f[{n}]")
+        Jx, Ju = e.jac(x, u, p)
+        assert_close(aos(Jx, 13, 13)[0], c["Jx"], RTOL, what=f"id Jx[{n}]")
+        out = e.rollout(x, u, 1, c["h"], okb.U_CONST, p=p)
+        assert_close(aos(out["xf"])[0], c["xn"], RTOL, what=f"id xn[{n}]")
+    e.close()
+
+
+def test_rigid_body_golden(okb, params, golden):
+    c = golden["rigid_body"]
+    e = okb.Engine(params, okb.RIGID_BODY)
+    x, u = soa([c["x"]]), soa([c["u"]])
+    assert_close(aos(e.rhs(x, u))[0], c["f"], RTOL, what="rb f")
+    Jx, Ju = e.jac(x, u)
+    assert_close(aos(Jx, 13, 13)[0], c["Jx"], RTOL, what="rb Jx")
+    assert float(Ju.abs().max()) == 0.0
+    xn, Phi, Gam = e.sens_step(x, u, c["h"])
+    assert_close(aos(xn)[0], c["xn"], RTOL, what="rb xn")
+    assert_close(aos(Phi, 13, 13)[0], c["Phi"], RTOL, what="rb Phi")
+    e.close()
+
+
+# ---------------------------------------------------------------- oracle, seeded batches -----------
+def test_rhs_jac_vs_oracle_batch(eng, oracle):
+    B = 4099                                   # ragged: not a multiple of the block size
+    x = oracle.synth_x0(0, B)
+    u = oracle.synth_controls(0, B, 1)[:, 0, :]
+    f = aos(eng.rhs(soa(x), soa(u))); Jx, Ju = eng.jac(soa(x), soa(u))
+    assert_close(f, oracle.rhs(x, u), RTOL, what="f batch")
+    jx, ju = oracle.jac(x, u)
+    assert_close(aos(Jx, 13, 13), jx, RTOL, what="Jx batch")
+    assert_close(aos(Ju, 13, 3), ju, RTOL, what="Ju batch")
+
+
+def test_synth_inputs_bit_identical(eng, oracle):
+    B, N, i0 = 1000, 7, 12345
+    x0, u = eng.synth_inputs(B, N, index0=i0)
+    assert np.array_equal(aos(x0), oracle.synth_x0(i0, B))
+    assert np.array_equal(u.cpu().numpy().transpose(2, 0, 1), oracle.synth_controls(i0, B, N))
+
+
+@pytest.mark.parametrize("mode", ["const", "per_step", "shared", "synth"])
+def test_rollout_vs_oracle(eng, oracle, okb, mode):
+    B, N, h = 777, 200, 1e-3
+    x0 = oracle.synth_x0(5000, B)
+    uall = oracle.synth_controls(5000, B, N)                # [B][N][3]
+    if mode == "const":
+        ref = oracle.rollout(x0, uall[:, 0, :].copy(), N, h, u_mode=0)
+        out = eng.rollout(soa(x0), soa(uall[:, 0, :]), N, h, okb.U_CONST)
+    elif mode == "per_step":
+        ref = oracle.rollout(x0, uall, N, h, u_mode=1)
+        u_d = torch.from_numpy(np.ascontiguousarray(uall.transpose(1, 2, 0))).cuda()     # [N][3][B]
+        out = eng.rollout(soa(x0), u_d, N, h, okb.U_PER_STEP)
+    elif mode == "shared":
+        ref = oracle.rollout(x0, uall[0].copy(), N, h, u_mode=2)
+        out = eng.rollout(soa(x0), torch.from_numpy(uall[0].copy()).cuda(), N, h, okb.U_SHARED)
+    else:
+        ref = oracle.rollout(None, None, N, h, u_mode=3, traj0=5000, n=B)
+        out = eng.rollout(None, None, N, h, okb.U_SYNTH, index0=5000, B=B)
+    assert int(out["status"].sum()) == 0
+    assert_close(aos(out["xf"]), ref, RTOL, what=f"rollout {mode}")
+
+
+def test_rollout_empty_and_single(eng, okb):
+    out = eng.rollout(torch.empty(13, 0, dtype=torch.float64, device="cuda"),
+                      torch.empty(3, 0, dtype=torch.float64, device="cuda"), 10, 1e-3, okb.U_CONST)
+    assert out["xf"].shape == (13, 0)
+
+
+def test_rollout_flags_nonfinite(eng, okb, oracle):
+    x0 = oracle.synth_x0(0, 4)
+    x0[2, 6:9] = 0.0                            # |r| = 0 -> division by zero in the tether term
+    out = eng.rollout(soa(x0), soa(np.zeros((4, 3))), 3, 1e-3, okb.U_CONST)
+    st = out["status"].cpu().numpy()
+    ref = oracle.rollout(x0, np.zeros((4, 3)), 3, 1e-3)
+    assert list(st) == [0, 0, 1, 0]
+    assert np.array_equal(np.isfinite(ref).all(1), st == 0)        # same non-finite set as the oracle
+
+
+def test_sharding_bitwise_identical(eng, okb):
+    """1-GPU vs sharded evaluation must agree bit for bit per global trajectory index."""
+    N, h = 50, 1e-3
+    full = eng.rollout(None, None, N, h, okb.U_SYNTH, index0=0, B=4096)["xf"]
+    parts = [eng.rollout(None, None, N, h, okb.U_SYNTH, index0=o, B=b)["xf"] for o, b in ((0, 1000), (1000, 2072), (3072, 1024))]
+    assert torch.equal(full, torch.cat(parts, dim=1))
+
+
+def test_rollout_host_pipeline(eng, okb, oracle):
+    B, N, h = 3000, 40, 1e-3
+    x0 = oracle.synth_x0(0, B); uall = oracle.synth_controls(0, B, N)
+    x0_h = torch.from_numpy(np.ascontiguousarray(x0.T)).pin_memory()
+    u_h = torch.from_numpy(np.ascontiguousarray(uall.transpose(1, 2, 0))).pin_memory()
+    xf_h = torch.empty(13, B, dtype=torch.float64).pin_memory()
+    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    eng.rollout_host(x0_h, u_h, N, h, okb.U_PER_STEP, xf_h, status_h=st_h)
+    ref = oracle.rollout(x0, uall, N, h, u_mode=1)
+    assert_close(xf_h.numpy().T, ref, RTOL, what="host pipeline rollout")
+    assert int(st_h.sum()) == 0
+
+
+def test_sens_rollout_vs_oracle(eng, oracle):
+    """config 3 shape: NMPC horizon N = 10.  h = 0.02: explicit RK4 is unstable for this model at h >= 0.05
+    (the oracle itself overflows), so the survey's h = 0.1 is not a usable multiple-shooting step."""
+    B, N, h = 130, 10, 0.02
+    x0 = oracle.synth_x0(100, B); uall = oracle.synth_controls(100, B, N)
+    xs, Phi, Gam = eng.sens_rollout(soa(x0), torch.from_numpy(np.ascontiguousarray(uall.transpose(1, 2, 0))).cuda(), h)
+    rxs, rPhi, rGam = oracle.rk4_sens_rollout(x0, uall, h)
+    assert_close(xs.cpu().numpy().transpose(2, 0, 1), rxs, RTOL, what="sens rollout states")
+    assert_close(Phi.cpu().numpy().transpose(2, 0, 1).reshape(B, N, 13, 13), rPhi, RTOL, what="Phi")
+    assert_close(Gam.cpu().numpy().transpose(2, 0, 1).reshape(B, N, 13, 3), rGam, RTOL, what="Gamma")
+
+
+def test_sens_linearity_property(eng, oracle):
+    """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
+    B, h = 2048, 0.02
+    x = oracle.synth_x0(0, B); u = oracle.synth_controls(0, B, 1)[:, 0, :]
+    rng = np.random.default_rng(1)
+    dx = 1e-6 * rng.standard_normal((B, 13)); du = 1e-6 * rng.standard_normal((B, 3))
+    xn, Phi, Gam = eng.sens_step(soa(x), soa(u), h)
+    xn2, _, _ = eng.sens_step(soa(x + dx), soa(u + du), h)
+    pred = aos(xn) + np.einsum("bij,bj->bi", aos(Phi, 13, 13), dx) + np.einsum("bij,bj->bi", aos(Gam, 13, 3), du)
+    assert np.abs(pred - aos(xn2)).max() < 1e-9
+
+
+def test_colloc_vs_oracle_batch_with_param_perturbation(eng, oracle, golden, yaml_path):
+    """config 4 shape: NMPC collocation (P=5,S=2, nmpf_node scaling), per-scenario aero perturbation."""
+    from oracle.oracle_py import params_from_yaml
+    c = golden["colloc_nmpc_P5_S2_scaled"]
+    B, M = 200, 11
+    rng = np.random.default_rng(2)
+    z = np.array(c["z"])[None, :] * (1 + 0.01 * rng.standard_normal((B, 209)))
+    prm = params_from_yaml(yaml_path)
+    prm_b = np.tile(prm, (B, 1))
+    idx21 = [9, 10, 12, 13, 14, 15, 17, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32]   # 21 id coefficients inside the 39-vector
+    scale = 1 + 0.1 * (2 * rng.random((B, 21)) - 1)
+    prm_b[:, idx21] *= scale
+    p21 = prm_b[:, idx21]
+    compD = oracle.cheb_compdiff(5, 2)
+    G, JX, JU, gn = eng.colloc_eval(soa(z), M, compD, 0.25, c["sx"], c["su"], p=soa(p21))
+    rG, rJX, rJU = oracle.colloc_eval(z, 5, 2, 0.0, 1.0, c["sx"], c["su"], prm_batch=prm_b)
+    assert_close(aos(G), rG, RTOL, what="G batch")
+    assert_close(aos(JX, M, 15, 15), rJX, RTOL, what="JX batch")
+    assert_close(aos(JU, M, 15, 4), rJU, RTOL, what="JU batch")
+
+
+def test_ekf_predict_vs_oracle_batch(eng, oracle):
+    B, dt = 515, 0.0084
+    x = oracle.synth_x0(0, B); u = oracle.synth_controls(0, B, 1)[:, 0, :]
+    W, V = oracle.ekf_defaults()
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((B, 13, 13)) * 0.1
+    P = 10 * W[None] + A @ A.transpose(0, 2, 1)
+    xn, Pn = eng.ekf_predict(soa(x), soa(u), dt, soa(P.reshape(B, 169)), W)
+    rxn, rPn = oracle.ekf_predict(x, u, dt, P, W)
+    assert_close(aos(xn), rxn, RTOL, what="ekf xn batch")
+    assert_close(aos(Pn, 13, 13), rPn, RTOL, what="ekf Pn batch")
+    # update step
+    z = x[:, 6:13] + 0.01 * rng.standard_normal((B, 7))
+    xu, Pu = eng.ekf_update(soa(z), V, xn.clone(), Pn.clone())
+    rxu, rPu = oracle.ekf_update(z, V, rxn, rPn)
+    assert_close(aos(xu), rxu, 1e-8, what="ekf update x")
+    assert_close(aos(Pu, 13, 13), rPu, 1e-8, scale=1e-3, what="ekf update P")
+
+
+def test_id_cost_rollout_vs_oracle(okb, params, oracle, golden):
+    """config 5 shape: parameter samples x shared control log, id-variant RHS, fused fitting cost."""
+    e = okb.Engine(params, okb.KITE_ID)
+    B, N, h = 300, 100, 1e-3
+    c = golden["rhs_id"]["nominal"]
+    pnom = np.array(c["p"])
+    rng = np.random.default_rng(4)
+    p = pnom[None] * (1 + 0.1 * (2 * rng.random((B, 21)) - 1))
+    p[0] = pnom
+    x0 = np.array(golden["rollout_config1"]["x0"])
+    k = np.arange(N)
+    u = np.stack([0.1 * np.ones(N), 0.1 * np.sign(np.sin(0.37 * k)), 0.1 * np.sign(np.sin(0.23 * k + 1))], 1)   # PRBS-like
+    _, ytraj = oracle.rollout(x0, u, N, h, u_mode=2, p=pnom, kind=1, want_traj=True)
+    y = ytraj[0, 1:, :].copy()
+    rcost, rxf = oracle.id_cost_rollout(x0, u, y, p, h)
+    x0b = np.tile(x0, (B, 1))
+    out = e.rollout(soa(x0b), torch.from_numpy(u.copy()).cuda(), N, h, okb.U_SHARED, p=soa(p), y=torch.from_numpy(y).cuda())
+    assert_close(aos(out["xf"]), rxf, RTOL, what="id xf")
+    cost = out["cost"].cpu().numpy()
+    assert cost[0] < 1e-20                        # nominal parameters reproduce the measurement
+    assert_close(cost, rcost, 1e-9, scale=1e-9, what="id cost")
+    e.close()
+
+
+def test_error_paths(eng, okb):
+    x = torch.zeros(13, 4, dtype=torch.float64, device="cuda")
+    with pytest.raises(okb.KiteError):
+        eng.rhs(x, None)                                      # u required
+    L = okb.load_library()
+    assert L.kite_rhs_batch(None, 1, 1, None, None, None, None) != 0
