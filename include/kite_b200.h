@@ -183,6 +183,9 @@ int kite_comm_destroy(kite_ctx* ctx);
 /* Register-resident dependent-DFMA microbenchmark: returns measured FP64 FMA throughput in TFLOP/s
  * (FMA = 2 flops) over `iters` iterations; the roofline denominator reported by bench.py. */
 int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out);
+/* Accuracy self-test of the engine's lean special functions on the device (MUFU seed + refinement):
+ * out[i] = f(x[i]) with which = 0: 1/x, 1: 1/sqrt(x), 2: asin(x) for |x| <= 0.6, 3: 1/(1+exp(-x)). */
+int kite_math_selftest(kite_ctx* ctx, long n, const double* x_d, double* out_d, int which);
 
 #ifdef __cplusplus
 }

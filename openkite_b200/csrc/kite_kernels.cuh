@@ -563,4 +563,20 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 }
 constexpr long FP64_PEAK_FMAS_PER_ITER = 64;
 
+// Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic.
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256) k_math_selftest(const double* __restrict__ x, double* __restrict__ out, long n, int which) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = x[i];
+    double r;
+    switch (which) {
+        case 0: r = fast_rcp(a); break;
+        case 1: r = fast_rsqrt(a); break;
+        case 2: r = asin_poly(a); break;
+        default: r = fast_logistic(a); break;
+    }
+    out[i] = r;
+}
+
 }  // namespace kite

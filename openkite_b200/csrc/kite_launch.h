@@ -13,6 +13,7 @@ void launch_ekf_state_jac(const EkfArgs& a, bool rigid, cudaStream_t s);
 void launch_ekf_cov(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
 void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s);
+void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s);
 void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s);
 inline unsigned blocks_for(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 }  // namespace kite

@@ -16,6 +16,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "kite_math.cuh"
+
 namespace kite {
 
 // Derived aerodynamic coefficients (from the 21 raw coefficients, kite.cpp:571-572 order).
@@ -107,17 +109,26 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     const double a[3] = {x[10], x[11], x[12]};
     const double dE = u[1], dR = u[2];
 
-    // ---- airspeed, angles -------------------------------------------------------------
+    // ---- airspeed, angles (lean special functions, kite_math.cuh) ------------------------------
     const double V2 = fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2]));
-    const double V = sqrt(V2);
-    const double iVe = 1.0 / (V + K.eps);
-    const double sb = v[1] * iVe;                 // sin(sideslip)
-    const double ss = asin(sb);
-    const double cb = sqrt(fma(-sb, sb, 1.0));    // cos(sideslip) >= 0
+    const double rV = fast_rsqrt(V2);                         // 1/V (also d V/d v = v rV in the Jacobian)
+    const double V = (V2 > 0.0) ? V2 * rV : 0.0;              // v = 0 is a legal state of the standard model
+    const double iVe = fast_rcp(V + K.eps);
+    const double sb = v[1] * iVe;                             // sin(sideslip)
+    const double c2 = fma(-sb, sb, 1.0);
+    const double rcb = fast_rsqrt(c2);                        // 1/cos(sideslip)
+    const double cb = (c2 > 0.0) ? c2 * rcb : 0.0;            // cos(sideslip) >= 0
     const double xe = v[0] + K.eps;
-    const double aoa = atan2(v[2], xe);
-    const double irho = rsqrt(fma(xe, xe, v[2] * v[2]));
-    const double ca = xe * irho, sa = v[2] * irho;   // cos/sin(angle of attack)
+    const double irho = fast_rsqrt(fma(xe, xe, v[2] * v[2]));
+    const double ca = xe * irho, sa = v[2] * irho;            // cos/sin(angle of attack)
+    double ss, aoa;
+    if (fabs(sb) <= KITE_ASIN_FAST_MAX && fabs(sa) <= KITE_ASIN_FAST_MAX && xe > 0.0) {
+        ss = asin_poly(sb);                                   // both angles within +-36.8 deg: two interleaved
+        aoa = asin_poly(sa);                                  // polynomial chains, no division, no branches
+    } else {
+        ss = asin(sb);                                        // post-stall / backwards flight: libm, any quadrant
+        aoa = atan2(v[2], xe);
+    }
     const double qS = K.cqS * V2;
 
     // ---- aerodynamic force in the wind frame, rotated to body ---------------------------
@@ -153,11 +164,11 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
 
     // ---- tether: R = -tau n, tau = (Ks (d-Lt) + Kd n.vi) * logistic(4 (d-Lt)) -------------
     const double d2 = fma(r[0], r[0], fma(r[1], r[1], r[2] * r[2]));
-    const double id = rsqrt(d2);
+    const double id = fast_rsqrt(d2);
     const double d = d2 * id;
     const double n[3] = {r[0] * id, r[1] * id, r[2] * id};
     const double e = d - K.Lt;
-    const double H = 1.0 / (1.0 + exp(-4.0 * e));
+    const double H = fast_logistic(4.0 * e);                  // K/(1+exp(-4x)), kitemath.cpp:31-34
     const double nv = fma(n[0], vi[0], fma(n[1], vi[1], n[2] * vi[2]));
     const double tens = fma(K.Ks, e, K.Kd * nv);
     const double tau = tens * H;
@@ -208,9 +219,8 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
 
     if constexpr (JAC) {
         // =========================== gradients w.r.t. v of the aero scalars =======================
-        const double iV = 1.0 / V;
-        const double dV[3] = {v[0] * iV, v[1] * iV, v[2] * iV};
-        const double icb = 1.0 / cb;
+        const double dV[3] = {v[0] * rV, v[1] * rV, v[2] * rV};
+        const double icb = rcb;
         // d sb = iVe (e1 - sb dV);  d ss = d sb / cb
         double dss[3];
 #pragma unroll
@@ -478,22 +488,24 @@ __device__ __forceinline__ void model_eval(const KiteConsts& K, const AeroCoef& 
 template <bool RIGID>
 __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A, double (&x)[13], const double (&u)[3],
                                          double h) {
+    // The four stages run as a real loop (one copy of the RHS in the instruction stream: the fully unrolled body
+    // was ~100 KB of SASS and stalled on instruction fetch, profiles/r1a_rollout_ncu_summary.txt).
     NoSink ns;
     double k[13], acc[13], xt[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) { acc[i] = 0.0; xt[i] = x[i]; }
     const double hh = 0.5 * h;
-    model_eval<RIGID, false>(K, A, x, u, k, ns);
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        model_eval<RIGID, false>(K, A, xt, u, k, ns);
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;     // tableau weights b = (1,2,2,1)/6
+        const double an = (st == 2) ? h : hh;                    // next stage offset a = (1/2, 1/2, 1)
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { acc[i] = k[i]; xt[i] = fma(hh, k[i], x[i]); }
-    model_eval<RIGID, false>(K, A, xt, u, k, ns);
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { acc[i] = fma(2.0, k[i], acc[i]); xt[i] = fma(hh, k[i], x[i]); }
-    model_eval<RIGID, false>(K, A, xt, u, k, ns);
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { acc[i] = fma(2.0, k[i], acc[i]); xt[i] = fma(h, k[i], x[i]); }
-    model_eval<RIGID, false>(K, A, xt, u, k, ns);
+        for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], x[i]); }
+    }
     const double h6 = h / 6.0;
 #pragma unroll
-    for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i] + k[i], x[i]);
+    for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }
 
 // ---- counter-based synthetic inputs (workload definition; identical to oracle::counter_uniform) ----

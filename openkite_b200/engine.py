@@ -94,6 +94,7 @@ def load_library():
     L.kite_allgather.argtypes = [vp, dp, dp, lg]
     L.kite_comm_destroy.argtypes = [vp]
     L.kite_fp64_peak.argtypes = [vp, ip, C.POINTER(db)]
+    L.kite_math_selftest.argtypes = [vp, lg, dp, dp, ip]
     _lib = L
     return L
 
@@ -269,6 +270,12 @@ class Engine:
         return x, P
 
     # ---- diagnostics ----------------------------------------------------------------------------
+    def math_selftest(self, x, which):
+        self._use_torch_stream()
+        out = torch.empty_like(x)
+        self._ck(self.L.kite_math_selftest(self.ctx, x.numel(), _ptr(x), _ptr(out), which))
+        return out
+
     def fp64_peak(self, iters=20000):
         self._use_torch_stream()
         out = C.c_double()

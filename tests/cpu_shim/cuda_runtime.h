@@ -12,4 +12,5 @@
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
-using std::fma; using std::sqrt; using std::asin; using std::atan2; using std::exp;
+#include <cstring>
+using std::fma; using std::sqrt; using std::asin; using std::atan2; using std::exp; using std::fabs; using std::fmin; using std::fmax;

@@ -308,6 +308,38 @@ def test_id_cost_rollout_vs_oracle(okb, params, oracle, golden):
     e.close()
 
 
+def test_lean_math_accuracy(eng):
+    """kite_math.cuh on the real MUFU seeds: <= 4 ulp-ish relative error over the ranges the model produces."""
+    rng = np.random.default_rng(7)
+    x = torch.from_numpy(np.concatenate([10.0 ** rng.uniform(-8, 8, 200000), [1.0, 2.0, 1e-4, 37.5]])).cuda()
+    for which, ref in ((0, lambda a: 1.0 / a), (1, lambda a: 1.0 / np.sqrt(a))):
+        got = eng.math_selftest(x, which).cpu().numpy()
+        r = ref(x.cpu().numpy())
+        assert np.abs(got / r - 1).max() < 1e-15, which
+    xa = torch.from_numpy(rng.uniform(-0.6, 0.6, 200000)).cuda()
+    got = eng.math_selftest(xa, 2).cpu().numpy()
+    assert np.abs(got - np.arcsin(xa.cpu().numpy())).max() < 4e-16
+    xl = torch.from_numpy(np.concatenate([rng.uniform(-60, 60, 200000), [-800.0, 800.0, 0.0]])).cuda()
+    got = eng.math_selftest(xl, 3).cpu().numpy()
+    xr = xl.cpu().numpy()
+    ref = np.where(xr >= 0, 1 / (1 + np.exp(-np.abs(xr))), np.exp(-np.abs(xr)) / (1 + np.exp(-np.abs(xr))))
+    assert np.abs(got - ref).max() < 1e-15
+    assert np.abs((got[ref > 1e-280] / ref[ref > 1e-280]) - 1).max() < 2e-15
+
+
+def test_rollout_post_stall_fallback(eng, okb, oracle):
+    """States outside the fast asin range (|aoa| or |sideslip| > 36.8 deg, backwards flight, v = 0) take the libm path."""
+    x0 = oracle.synth_x0(0, 6)
+    x0[0, 0:3] = [1.0, 0.2, 4.0]      # aoa ~ 76 deg
+    x0[1, 0:3] = [-3.0, 0.1, 0.5]     # flying backwards: aoa in the second quadrant
+    x0[2, 0:3] = [2.0, 3.0, 0.1]      # sideslip ~ 56 deg
+    x0[3, 0:3] = [0.0, 0.0, 0.0]      # at rest: legal for the standard model (1e-4 regularisers)
+    u = oracle.synth_controls(0, 6, 1)[:, 0, :]
+    assert_close(aos(eng.rhs(soa(x0), soa(u))), oracle.rhs(x0, u), RTOL, what="post-stall rhs")
+    out = eng.rollout(soa(x0), soa(u), 20, 1e-3, okb.U_CONST)
+    assert_close(aos(out["xf"]), oracle.rollout(x0, u, 20, 1e-3), RTOL, what="post-stall rollout")
+
+
 def test_error_paths(eng, okb):
     x = torch.zeros(13, 4, dtype=torch.float64, device="cuda")
     with pytest.raises(okb.KiteError):
