@@ -8,6 +8,8 @@
 // the constant bank as DFMA operands and cost no registers.
 // =====================================================================================
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "kite_model.cuh"
 
 namespace kite {
@@ -28,21 +30,29 @@ __host__ __device__ constexpr bool ju_nz(int i, int j) {
            (i == 1 && j == 2) || (i == 3 && j == 2) || (i == 5 && j == 2);
 }
 constexpr int JAC_SLOTS = JX_SLOTS + 7;   // 132
-struct SlotTab { int jx[13][13]; int ju[13][3]; };
+struct SlotTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
+constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7: the slots a zero-arm model touches are the first 111
 constexpr SlotTab make_slot_tab() {
     SlotTab t{};
     int s = 0;
     for (int i = 0; i < 13; ++i)
-        for (int j = 0; j < 13; ++j) t.jx[i][j] = jx_nz(i, j, true) ? s++ : -1;
+        for (int j = 0; j < 13; ++j) t.jx[i][j] = jx_nz(i, j, false) ? s++ : -1;
     for (int i = 0; i < 13; ++i)
         for (int j = 0; j < 3; ++j) t.ju[i][j] = ju_nz(i, j) ? s++ : -1;
+    for (int i = 0; i < 13; ++i)
+        for (int j = 0; j < 13; ++j)
+            if (jx_nz(i, j, true) && !jx_nz(i, j, false)) t.jx[i][j] = s++;
+    // slot of entry (row i, tangent column c) of [Jx | Ju]
+    for (int i = 0; i < 13; ++i)
+        for (int c = 0; c < 16; ++c) t.col[i][c] = (c < 13) ? t.jx[i][c] : t.ju[i][c - 13];
     return t;
 }
 __device__ constexpr SlotTab SLOT_TAB = make_slot_tab();
 __device__ __forceinline__ constexpr int jx_slot(int i, int j) { return SLOT_TAB.jx[i][j]; }
 __device__ __forceinline__ constexpr int ju_slot(int i, int j) { return SLOT_TAB.ju[i][j]; }
-static_assert(make_slot_tab().jx[12][12] == JX_SLOTS - 1, "slot numbering");
-static_assert(make_slot_tab().ju[5][2] == JAC_SLOTS - 1, "slot numbering");
+static_assert(make_slot_tab().jx[12][12] == 103, "slot numbering");
+static_assert(make_slot_tab().ju[5][2] == JAC_SLOTS_NOARM - 1, "slot numbering");
+static_assert(make_slot_tab().jx[5][12] == JAC_SLOTS - 1, "slot numbering");
 
 // Sink: compact slots, SoA over units.
 struct CompactSink {
@@ -123,8 +133,11 @@ struct RolloutArgs {
 
 constexpr int ROLLOUT_BLOCK = 128;
 
-template <int UMODE, bool RIGID, bool PERCOEF>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
+template <int UMODE, bool RIGID, bool PERCOEF, bool SMEM>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK, SMEM ? 4 : 3) k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
+    __shared__ double sh[SMEM ? 26 * ROLLOUT_BLOCK : 1];
+    double* const sx = sh + threadIdx.x;                              // state column of this thread   (SMEM variant)
+    double* const sacc = sh + 13 * ROLLOUT_BLOCK + threadIdx.x;       // tableau accumulator column
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.B) return;
     double x[13], u[3], un[3];
@@ -133,6 +146,10 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) k_rk4_rollout(const __grid_cons
     } else {
 #pragma unroll
         for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x0 + (long)c * a.ld + i);
+    }
+    if constexpr (SMEM) {
+#pragma unroll
+        for (int c = 0; c < 13; ++c) sx[c * ROLLOUT_BLOCK] = x[c];
     }
     AeroCoef A = a.K.A;
     if constexpr (PERCOEF) load_coef(a.K, a.p, a.ld, i, A);
@@ -167,21 +184,27 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) k_rk4_rollout(const __grid_cons
                 synth_control((uint64_t)(a.index0 + i), (uint64_t)(k + 1), un);
             }
         }
-        rk4_step<RIGID>(a.K, A, x, u, a.h);
+        if constexpr (SMEM) rk4_step_smem<RIGID>(a.K, A, sx, sacc, ROLLOUT_BLOCK, u, a.h);
+        else rk4_step<RIGID>(a.K, A, x, u, a.h);
         if (a.y) {                                  // uniform branch: identification cost fused into the rollout
             double e = 0.0;
 #pragma unroll
             for (int c = 0; c < 13; ++c) {
-                const double dlt = __ldg(a.y + k * 13 + c) - x[c];
+                const double xc = SMEM ? sx[c * ROLLOUT_BLOCK] : x[c];
+                const double dlt = __ldg(a.y + k * 13 + c) - xc;
                 e = fma(Qc[c] * dlt, dlt, e);
             }
             cost += e;
         }
         if (a.traj && k + 1 == next_save) {
 #pragma unroll
-            for (int c = 0; c < 13; ++c) a.traj[((long)saved * 13 + c) * a.ld + i] = x[c];
+            for (int c = 0; c < 13; ++c) a.traj[((long)saved * 13 + c) * a.ld + i] = SMEM ? sx[c * ROLLOUT_BLOCK] : x[c];
             ++saved; next_save += a.save_every;
         }
+    }
+    if constexpr (SMEM) {
+#pragma unroll
+        for (int c = 0; c < 13; ++c) x[c] = sx[c * ROLLOUT_BLOCK];
     }
 #pragma unroll
     for (int c = 0; c < 13; ++c) a.xf[(long)c * a.ld + i] = x[c];
@@ -232,98 +255,138 @@ __global__ void __launch_bounds__(128) k_sens_stage_jac(const __grid_constant__ 
     if (i >= a.B) return;
     double x[13], u[3], k[13], acc[13], xt[13];
 #pragma unroll
-    for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x + (long)c * a.ld + i);
+    for (int c = 0; c < 13; ++c) { x[c] = __ldg(a.x + (long)c * a.ld + i); xt[c] = x[c]; acc[c] = 0.0; }
 #pragma unroll
     for (int c = 0; c < 3; ++c) u[c] = __ldg(a.u + (long)c * a.ld + i);
     const double hh = 0.5 * a.h;
     const long stage_stride = (long)JAC_SLOTS * a.ld;
-    {
-        CompactSink s{a.Jw + i, a.ld};
-        model_eval<RIGID, true>(a.K, a.K.A, x, u, k, s);
-    }
-#pragma unroll
-    for (int c = 0; c < 13; ++c) { acc[c] = k[c]; xt[c] = fma(hh, k[c], x[c]); }
-    {
-        CompactSink s{a.Jw + stage_stride + i, a.ld};
+    // stage loop kept rolled: one copy of the f + Jacobian code in the instruction stream (the 4x unrolled body
+    // stalled on instruction fetch: no_instruction 1.34 per issue in profiles/r1a)
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        CompactSink s{a.Jw + st * stage_stride + i, a.ld};
         model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, s);
-    }
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+        const double an = (st == 2) ? a.h : hh;
 #pragma unroll
-    for (int c = 0; c < 13; ++c) { acc[c] = fma(2.0, k[c], acc[c]); xt[c] = fma(hh, k[c], x[c]); }
-    {
-        CompactSink s{a.Jw + 2 * stage_stride + i, a.ld};
-        model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, s);
-    }
-#pragma unroll
-    for (int c = 0; c < 13; ++c) { acc[c] = fma(2.0, k[c], acc[c]); xt[c] = fma(a.h, k[c], x[c]); }
-    {
-        CompactSink s{a.Jw + 3 * stage_stride + i, a.ld};
-        model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, s);
+        for (int c = 0; c < 13; ++c) { acc[c] = fma(wgt, k[c], acc[c]); xt[c] = fma(an, k[c], x[c]); }
     }
     const double h6 = a.h / 6.0;
 #pragma unroll
-    for (int c = 0; c < 13; ++c) a.xn[(long)c * a.ld + i] = fma(h6, acc[c] + k[c], x[c]);
+    for (int c = 0; c < 13; ++c) a.xn[(long)c * a.ld + i] = fma(h6, acc[c], x[c]);
 }
 
-// slot of entry (row i, tangent column c) of [Jx | Ju], or -1 when structurally zero
-__device__ __forceinline__ int jac_col_slot(int i, int c, bool arm, bool rigid) {
-    if (c < 13) {
-        bool nz = rigid ? (i >= 6 && jx_nz(i, c, false)) : jx_nz(i, c, arm);
-        return nz ? jx_slot(i, c) : -1;
+// ---- kernel B: tangent propagation ---------------------------------------------------------------------
+// CTA = 256 threads = 32 units x 8 lanes; lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] (13 state seeds,
+// 3 control seeds).  Per stage the unit's compact Jacobian is staged global -> shared with cp.async (coalesced
+// 256 B rows, double buffered against the previous stage's FMAs), transposed to tile[unit][slot] so that the 8 lanes
+// of a unit read it back as broadcast LDS.128 (two entries per load, 1 load per 4 DFMA).  S, S_next and the tableau
+// accumulator (3 x 13 x 2 doubles) live in registers; results leave through shared memory as coalesced 256 B rows.
+constexpr int SENS_UNITS = 32;                 // units per CTA
+constexpr int SENS_TS = 134;                   // tile row stride in doubles (even: 16 B aligned rows; 134 mod 32 banks spread)
+constexpr int SENS_THREADS = 256;
+
+struct SensSmem {
+    double tile[2][SENS_UNITS * SENS_TS];      // double-buffered stage Jacobians; reused as the output staging area
+    short col_slot[13][16];
+};
+
+template <bool ARM, bool RIGID>
+__device__ __forceinline__ void sens_fill_tile(double* __restrict__ tile, const double* __restrict__ Jst, long ld, long unit0,
+                                               long B, int tid) {
+    constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;
+    const int u = tid & 31;
+    if (unit0 + u < B) {
+        const double* src = Jst + unit0 + u;
+        double* dst = tile + u * SENS_TS;
+#pragma unroll 4
+        for (int sl = tid >> 5; sl < NS; sl += SENS_THREADS / 32) {
+            __pipeline_memcpy_async(dst + sl, src + (long)sl * ld, 8);
+        }
     }
-    if (rigid) return -1;
-    return ju_nz(i, c - 13) ? ju_slot(i, c - 13) : -1;
+    __pipeline_commit();
 }
 
 template <bool ARM, bool RIGID>
-__global__ void __launch_bounds__(256) k_sens_propagate(const __grid_constant__ SensArgs a) {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long unit = t >> 4;
-    const int c = (int)(t & 15);           // tangent column owned by this lane
-    if (unit >= a.B) return;
+__global__ void __launch_bounds__(SENS_THREADS, 1) k_sens_propagate(const __grid_constant__ SensArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SensSmem& sm = *reinterpret_cast<SensSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lu = tid >> 3;                       // unit within the CTA (8 consecutive lanes share a unit)
+    const int l = tid & 7;
+    const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane
+    const long unit0 = (long)blockIdx.x * SENS_UNITS;
+    const long unit = unit0 + lu;
+    const bool live = unit < a.B;
     const long stage_stride = (long)JAC_SLOTS * a.ld;
-    const double* __restrict__ J = a.Jw + unit;
-    double S[13], Sn[13], acc[13];
+    for (int t = tid; t < 13 * 16; t += SENS_THREADS) sm.col_slot[t / 16][t % 16] = (short)SLOT_TAB.col[t / 16][t % 16];
+    sens_fill_tile<ARM, RIGID>(sm.tile[0], a.Jw, a.ld, unit0, a.B, tid);
+
+    double S0[13], S1[13], N0[13], N1[13], A0[13], A1[13];
     const double coef[4] = {0.0, 0.5 * a.h, 0.5 * a.h, a.h};
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
-        const double* __restrict__ Js = J + st * stage_stride;
-        // column c of [Jx | Ju] at this stage (lane-dependent slot; 13 scattered loads)
+        if (st < 3) sens_fill_tile<ARM, RIGID>(sm.tile[(st + 1) & 1], a.Jw + (st + 1) * stage_stride, a.ld, unit0, a.B, tid);
+        if (st < 3) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+        __syncthreads();                           // stage st tile complete and visible
+        const double* __restrict__ T = sm.tile[st & 1] + lu * SENS_TS;
+        // columns c0, c1 of [Jx | Ju] at this stage
 #pragma unroll
         for (int i = 0; i < 13; ++i) {
-            int sl = -1;
-            // resolve the slot with compile-time i and run-time c through a tiny switch-free table
-#pragma unroll
-            for (int cc = 0; cc < 16; ++cc)
-                if (cc == c) sl = jac_col_slot(i, cc, ARM, RIGID);
-            Sn[i] = (sl >= 0) ? __ldg(Js + (long)sl * a.ld) : 0.0;
+            const int s0 = sm.col_slot[i][c0], s1 = sm.col_slot[i][c1];
+            const bool z0 = (s0 < 0) || (!ARM && s0 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c0 >= 13));
+            const bool z1 = (s1 < 0) || (!ARM && s1 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c1 >= 13));
+            N0[i] = z0 ? 0.0 : T[z0 ? 0 : s0];
+            N1[i] = z1 ? 0.0 : T[z1 ? 0 : s1];
         }
         if (st > 0) {
             const double ah = coef[st];
-            // Sn += ah * Jx * S   (sparse, entries broadcast to the 16 lanes of a unit)
 #pragma unroll
             for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
-                double s = 0.0;
+                double p0 = 0.0, p1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 13; ++j) {
-                    if (jx_nz(i, j, ARM) && !(RIGID && i < 6)) s = fma(__ldg(Js + (long)jx_slot(i, j) * a.ld), S[j], s);
+                    if (jx_nz(i, j, ARM)) {
+                        const double jv = T[jx_slot(i, j)];       // adjacent slots: merged into LDS.128 by the compiler
+                        p0 = fma(jv, S0[j], p0);
+                        p1 = fma(jv, S1[j], p1);
+                    }
                 }
-                Sn[i] = fma(ah, s, Sn[i]);
+                N0[i] = fma(ah, p0, N0[i]);
+                N1[i] = fma(ah, p1, N1[i]);
             }
         }
         const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
 #pragma unroll
         for (int i = 0; i < 13; ++i) {
-            acc[i] = (st == 0) ? Sn[i] : fma(wgt, Sn[i], acc[i]);
-            S[i] = Sn[i];
+            A0[i] = (st == 0) ? N0[i] : fma(wgt, N0[i], A0[i]);
+            A1[i] = (st == 0) ? N1[i] : fma(wgt, N1[i], A1[i]);
+            S0[i] = N0[i]; S1[i] = N1[i];
         }
+        __syncthreads();                           // everyone done with tile[st&1] before it is refilled / reused
     }
+    // results -> shared [row r = component][unit] -> coalesced 256 B rows
+    double* out = sm.tile[0];                      // 208 rows x 32 units = 6656 doubles <= 2 x 4288
     const double h6 = a.h / 6.0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
-        const double val = fma(h6, acc[i], (i == c) ? 1.0 : 0.0);
-        if (c < 13) a.Phi[(long)(i * 13 + c) * a.ld + unit] = val;
-        else a.Gamma[(long)(i * 3 + (c - 13)) * a.ld + unit] = val;
+        const double v0 = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+        const double v1 = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
+        const int r0 = (c0 < 13) ? (i * 13 + c0) : (169 + i * 3 + (c0 - 13));
+        const int r1 = (c1 < 13) ? (i * 13 + c1) : (169 + i * 3 + (c1 - 13));
+        out[r0 * SENS_UNITS + lu] = v0;
+        out[r1 * SENS_UNITS + lu] = v1;
     }
+    __syncthreads();
+    const int u = tid & 31;
+    if (unit0 + u < a.B) {
+        for (int r = tid >> 5; r < 208; r += SENS_THREADS / 32) {
+            const double v = out[r * SENS_UNITS + u];
+            if (r < 169) a.Phi[(long)r * a.ld + unit0 + u] = v;
+            else a.Gamma[(long)(r - 169) * a.ld + unit0 + u] = v;
+        }
+    }
+    (void)live;
 }
 
 // ================================================================================================

@@ -508,6 +508,36 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A,
     for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }
 
+// Same step with the state x and the tableau accumulator parked in shared memory ([13][blockDim] columns, conflict
+// free) between stages: only the stage input and the RHS temporaries stay in registers, which buys a fourth
+// resident block per SM (128 instead of 168 registers).  sx/sacc point at this thread's column; stride = blockDim.
+template <bool RIGID>
+__device__ __forceinline__ void rk4_step_smem(const KiteConsts& K, const AeroCoef& A, double* __restrict__ sx,
+                                              double* __restrict__ sacc, int stride, const double (&u)[3], double h) {
+    NoSink ns;
+    double k[13], xt[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) xt[i] = sx[i * stride];
+    const double hh = 0.5 * h;
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        model_eval<RIGID, false>(K, A, xt, u, k, ns);
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+        const double an = (st == 2) ? h : hh;
+        if (st == 0) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { sacc[i * stride] = k[i]; xt[i] = fma(an, k[i], sx[i * stride]); }
+        } else if (st < 3) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { sacc[i * stride] = fma(wgt, k[i], sacc[i * stride]); xt[i] = fma(an, k[i], sx[i * stride]); }
+        } else {
+            const double h6 = h / 6.0;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) sx[i * stride] = fma(h6, sacc[i * stride] + k[i], sx[i * stride]);
+        }
+    }
+}
+
 // ---- counter-based synthetic inputs (workload definition; identical to oracle::counter_uniform) ----
 __host__ __device__ inline uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ULL;
