@@ -283,12 +283,16 @@ __global__ void __launch_bounds__(128) k_sens_stage_jac(const __grid_constant__ 
 // of a unit read it back as broadcast LDS.128 (two entries per load, 1 load per 4 DFMA).  S, S_next and the tableau
 // accumulator (3 x 13 x 2 doubles) live in registers; results leave through shared memory as coalesced 256 B rows.
 constexpr int SENS_UNITS = 32;                 // units per CTA
-constexpr int SENS_TS = 134;                   // tile row stride in doubles (even: 16 B aligned rows; 134 mod 32 banks spread)
+constexpr int SENS_TS = 133;                   // tile row stride in doubles: odd => the 32 units of a fill row and the 4 units of a
+                                               // broadcast read land in distinct banks (profiles/r1c: stride 134 had 4-way conflicts)
+constexpr int SENS_OS = 33;                    // output staging row stride (padded)
 constexpr int SENS_THREADS = 256;
 
+constexpr int SENS_RING = 4;                   // stage tiles in flight (cp.async ring): the next batch streams in behind the FMAs
+
 struct SensSmem {
-    double tile[2][SENS_UNITS * SENS_TS];      // double-buffered stage Jacobians; reused as the output staging area
-    short col_slot[13][16];
+    double tile[SENS_RING][SENS_UNITS * SENS_TS];   // ring of stage Jacobian tiles [unit][slot]
+    double out[208 * SENS_OS];                      // output staging [component row][unit]
 };
 
 template <bool ARM, bool RIGID>
@@ -300,93 +304,115 @@ __device__ __forceinline__ void sens_fill_tile(double* __restrict__ tile, const 
         const double* src = Jst + unit0 + u;
         double* dst = tile + u * SENS_TS;
 #pragma unroll 4
-        for (int sl = tid >> 5; sl < NS; sl += SENS_THREADS / 32) {
-            __pipeline_memcpy_async(dst + sl, src + (long)sl * ld, 8);
-        }
+        for (int sl = tid >> 5; sl < NS; sl += SENS_THREADS / 32) __pipeline_memcpy_async(dst + sl, src + (long)sl * ld, 8);
     }
-    __pipeline_commit();
 }
 
+// Persistent CTA: loops over batches of 32 units; tile t = batch * 4 + stage.  Tiles t+1..t+3 are always in flight.
 template <bool ARM, bool RIGID>
 __global__ void __launch_bounds__(SENS_THREADS, 1) k_sens_propagate(const __grid_constant__ SensArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SensSmem& sm = *reinterpret_cast<SensSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int lu = tid >> 3;                       // unit within the CTA (8 consecutive lanes share a unit)
+    const int lu = tid >> 3;                       // unit within the batch (8 consecutive lanes share a unit)
     const int l = tid & 7;
     const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane
-    const long unit0 = (long)blockIdx.x * SENS_UNITS;
-    const long unit = unit0 + lu;
-    const bool live = unit < a.B;
     const long stage_stride = (long)JAC_SLOTS * a.ld;
-    for (int t = tid; t < 13 * 16; t += SENS_THREADS) sm.col_slot[t / 16][t % 16] = (short)SLOT_TAB.col[t / 16][t % 16];
-    sens_fill_tile<ARM, RIGID>(sm.tile[0], a.Jw, a.ld, unit0, a.B, tid);
-
-    double S0[13], S1[13], N0[13], N1[13], A0[13], A1[13];
-    const double coef[4] = {0.0, 0.5 * a.h, 0.5 * a.h, a.h};
-#pragma unroll
-    for (int st = 0; st < 4; ++st) {
-        if (st < 3) sens_fill_tile<ARM, RIGID>(sm.tile[(st + 1) & 1], a.Jw + (st + 1) * stage_stride, a.ld, unit0, a.B, tid);
-        if (st < 3) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-        __syncthreads();                           // stage st tile complete and visible
-        const double* __restrict__ T = sm.tile[st & 1] + lu * SENS_TS;
-        // columns c0, c1 of [Jx | Ju] at this stage
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            const int s0 = sm.col_slot[i][c0], s1 = sm.col_slot[i][c1];
-            const bool z0 = (s0 < 0) || (!ARM && s0 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c0 >= 13));
-            const bool z1 = (s1 < 0) || (!ARM && s1 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c1 >= 13));
-            N0[i] = z0 ? 0.0 : T[z0 ? 0 : s0];
-            N1[i] = z1 ? 0.0 : T[z1 ? 0 : s1];
+    const long nbatch = (a.B + SENS_UNITS - 1) / SENS_UNITS;
+    const long my_batches = (nbatch > blockIdx.x) ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long ntiles = my_batches * 4;
+    auto issue = [&](long t) {                     // tile t of this CTA -> ring slot t % RING (always commits a group)
+        if (t < ntiles) {
+            const long batch = blockIdx.x + (t >> 2) * gridDim.x;
+            sens_fill_tile<ARM, RIGID>(sm.tile[t % SENS_RING], a.Jw + (t & 3) * stage_stride, a.ld, batch * SENS_UNITS, a.B, tid);
         }
-        if (st > 0) {
-            const double ah = coef[st];
+        __pipeline_commit();
+    };
+    for (int t = 0; t < SENS_RING - 1; ++t) issue(t);
+
+    // Stage recursion in "input tangent" form, which is uniform across lanes (no per-lane gather of Jacobian columns):
+    //   D_i = E + a_i h S_{i-1}   (E = seed matrix [I | 0]),   S_i = Jx_i D_i + Ju_i Eu   (Eu = [0 | I]),
+    //   [Phi | Gamma] = E + h/6 (S_1 + 2 S_2 + 2 S_3 + S_4).
+    // Each lane carries columns c0, c1 of D/S and of the accumulator; Jacobian entries are broadcast LDS.
+    double D0[13], D1[13], N0[13], N1[13], A0[13], A1[13];
+    double U0[3], U1[3];
 #pragma unroll
-            for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
-                double p0 = 0.0, p1 = 0.0;
+    for (int m = 0; m < 3; ++m) { U0[m] = (13 + m == c0) ? 1.0 : 0.0; U1[m] = (13 + m == c1) ? 1.0 : 0.0; }
+    const double h6 = a.h / 6.0;
+
+    for (long bi = 0; bi < my_batches; ++bi) {
+        const long unit0 = (blockIdx.x + bi * gridDim.x) * SENS_UNITS;
 #pragma unroll
-                for (int j = 0; j < 13; ++j) {
+        for (int j = 0; j < 13; ++j) { D0[j] = (j == c0) ? 1.0 : 0.0; D1[j] = (j == c1) ? 1.0 : 0.0; }
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            const long t = bi * 4 + st;
+            __pipeline_wait_prior(SENS_RING - 2);  // tile t landed (t+1, t+2 may still be in flight)
+            __syncthreads();                       // ... and is visible; everyone is past tile t-1, so its ring slot is free
+            issue(t + SENS_RING - 1);
+            const double* __restrict__ T = sm.tile[t % SENS_RING] + lu * SENS_TS;
+            // column-major traversal of the sparse Jacobian: for each input row j the (up to 13) entries J[i][j] update
+            // 26 independent accumulator chains N[i][c], so consecutive DFMAs never depend on each other
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+#pragma unroll
+                for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
                     if (jx_nz(i, j, ARM)) {
-                        const double jv = T[jx_slot(i, j)];       // adjacent slots: merged into LDS.128 by the compiler
-                        p0 = fma(jv, S0[j], p0);
-                        p1 = fma(jv, S1[j], p1);
+                        const double jv = T[jx_slot(i, j)];       // broadcast LDS.64 (4 distinct addresses per warp)
+                        N0[i] = fma(jv, D0[j], N0[i]);
+                        N1[i] = fma(jv, D1[j], N1[i]);
                     }
                 }
-                N0[i] = fma(ah, p0, N0[i]);
-                N1[i] = fma(ah, p1, N1[i]);
+            }
+            if (!RIGID) {
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        if (ju_nz(i, m)) {
+                            const double jv = T[ju_slot(i, m)];
+                            N0[i] = fma(jv, U0[m], N0[i]);
+                            N1[i] = fma(jv, U1[m], N1[i]);
+                        }
+                    }
+                }
+            }
+            const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+            const double an = (st == 2) ? a.h : 0.5 * a.h;        // a_{i+1} h, applied after stage i
+#pragma unroll
+            for (int i = 0; i < 13; ++i) {
+                A0[i] = (st == 0) ? N0[i] : fma(wgt, N0[i], A0[i]);
+                A1[i] = (st == 0) ? N1[i] : fma(wgt, N1[i], A1[i]);
+                if (st < 3) {
+                    D0[i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);
+                    D1[i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                }
             }
         }
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+        // results -> shared [row r = component][unit] (padded rows) -> coalesced 256 B rows
 #pragma unroll
         for (int i = 0; i < 13; ++i) {
-            A0[i] = (st == 0) ? N0[i] : fma(wgt, N0[i], A0[i]);
-            A1[i] = (st == 0) ? N1[i] : fma(wgt, N1[i], A1[i]);
-            S0[i] = N0[i]; S1[i] = N1[i];
+            const double v0 = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+            const double v1 = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
+            const int r0 = (c0 < 13) ? (i * 13 + c0) : (169 + i * 3 + (c0 - 13));
+            const int r1 = (c1 < 13) ? (i * 13 + c1) : (169 + i * 3 + (c1 - 13));
+            sm.out[r0 * SENS_OS + lu] = v0;
+            sm.out[r1 * SENS_OS + lu] = v1;
         }
-        __syncthreads();                           // everyone done with tile[st&1] before it is refilled / reused
-    }
-    // results -> shared [row r = component][unit] -> coalesced 256 B rows
-    double* out = sm.tile[0];                      // 208 rows x 32 units = 6656 doubles <= 2 x 4288
-    const double h6 = a.h / 6.0;
-#pragma unroll
-    for (int i = 0; i < 13; ++i) {
-        const double v0 = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
-        const double v1 = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
-        const int r0 = (c0 < 13) ? (i * 13 + c0) : (169 + i * 3 + (c0 - 13));
-        const int r1 = (c1 < 13) ? (i * 13 + c1) : (169 + i * 3 + (c1 - 13));
-        out[r0 * SENS_UNITS + lu] = v0;
-        out[r1 * SENS_UNITS + lu] = v1;
-    }
-    __syncthreads();
-    const int u = tid & 31;
-    if (unit0 + u < a.B) {
-        for (int r = tid >> 5; r < 208; r += SENS_THREADS / 32) {
-            const double v = out[r * SENS_UNITS + u];
-            if (r < 169) a.Phi[(long)r * a.ld + unit0 + u] = v;
-            else a.Gamma[(long)(r - 169) * a.ld + unit0 + u] = v;
+        __syncthreads();
+        const int u = tid & 31;
+        if (unit0 + u < a.B) {
+            for (int r = tid >> 5; r < 208; r += SENS_THREADS / 32) {
+                const double v = sm.out[r * SENS_OS + u];
+                if (r < 169) a.Phi[(long)r * a.ld + unit0 + u] = v;
+                else a.Gamma[(long)(r - 169) * a.ld + unit0 + u] = v;
+            }
         }
+        // the next iteration's first __syncthreads orders these reads of sm.out before it is overwritten again
     }
-    (void)live;
+    __pipeline_wait_prior(0);
 }
 
 // ================================================================================================

@@ -11,7 +11,11 @@ static void go_propagate(const SensArgs& a, cudaStream_t s) {
         cudaFuncSetAttribute(k_sens_propagate<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SensSmem));
         configured = true;
     }
-    k_sens_propagate<ARM, RIGID><<<blocks_for(a.B, SENS_UNITS), SENS_THREADS, sizeof(SensSmem), s>>>(a);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const unsigned nb = blocks_for(a.B, SENS_UNITS);
+    const unsigned grid = nb < (unsigned)sms ? nb : (unsigned)sms;      // persistent: one CTA per SM
+    k_sens_propagate<ARM, RIGID><<<grid, SENS_THREADS, sizeof(SensSmem), s>>>(a);
 }
 void launch_sens_propagate(const SensArgs& a, bool rigid, bool arm, cudaStream_t s) {
     if (rigid) go_propagate<false, true>(a, s);
