@@ -184,7 +184,8 @@ int kite_comm_destroy(kite_ctx* ctx);
  * (FMA = 2 flops) over `iters` iterations; the roofline denominator reported by bench.py. */
 int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out);
 /* Accuracy self-test of the engine's lean special functions on the device (MUFU seed + refinement):
- * out[i] = f(x[i]) with which = 0: 1/x, 1: 1/sqrt(x), 2: asin(x) for |x| <= 0.6, 3: 1/(1+exp(-x)). */
+ * out[i] = f(x[i]) with which = 0: 1/x, 1: 1/sqrt(x), 2: asin(x) for |x| <= 0.7072 (polynomial core),
+ * 3: 1/(1+exp(-x)), 4: asin(x) for |x| <= 1 through the (sin, cos) pair form the model uses. */
 int kite_math_selftest(kite_ctx* ctx, long n, const double* x_d, double* out_d, int which);
 
 #ifdef __cplusplus

@@ -134,10 +134,10 @@ struct RolloutArgs {
 constexpr int ROLLOUT_BLOCK = 128;
 
 template <int UMODE, bool RIGID, bool PERCOEF, bool SMEM>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK, SMEM ? 4 : 3) k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
-    __shared__ double sh[SMEM ? 26 * ROLLOUT_BLOCK : 1];
-    double* const sx = sh + threadIdx.x;                              // state column of this thread   (SMEM variant)
-    double* const sacc = sh + 13 * ROLLOUT_BLOCK + threadIdx.x;       // tableau accumulator column
+__global__ void __launch_bounds__(ROLLOUT_BLOCK, 3) k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
+    // SMEM: the step base state is parked in shared memory during the four stages (rk4_step_xsmem), [13][block] columns
+    __shared__ double sh[SMEM ? 13 * ROLLOUT_BLOCK : 1];
+    double* const sx = sh + threadIdx.x;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.B) return;
     double x[13], u[3], un[3];
@@ -146,10 +146,6 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK, SMEM ? 4 : 3) k_rk4_rollout(con
     } else {
 #pragma unroll
         for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x0 + (long)c * a.ld + i);
-    }
-    if constexpr (SMEM) {
-#pragma unroll
-        for (int c = 0; c < 13; ++c) sx[c * ROLLOUT_BLOCK] = x[c];
     }
     AeroCoef A = a.K.A;
     if constexpr (PERCOEF) load_coef(a.K, a.p, a.ld, i, A);
@@ -184,27 +180,22 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK, SMEM ? 4 : 3) k_rk4_rollout(con
                 synth_control((uint64_t)(a.index0 + i), (uint64_t)(k + 1), un);
             }
         }
-        if constexpr (SMEM) rk4_step_smem<RIGID>(a.K, A, sx, sacc, ROLLOUT_BLOCK, u, a.h);
+        if constexpr (SMEM) rk4_step_xsmem<RIGID>(a.K, A, sx, ROLLOUT_BLOCK, x, u, a.h);
         else rk4_step<RIGID>(a.K, A, x, u, a.h);
         if (a.y) {                                  // uniform branch: identification cost fused into the rollout
             double e = 0.0;
 #pragma unroll
             for (int c = 0; c < 13; ++c) {
-                const double xc = SMEM ? sx[c * ROLLOUT_BLOCK] : x[c];
-                const double dlt = __ldg(a.y + k * 13 + c) - xc;
+                const double dlt = __ldg(a.y + k * 13 + c) - x[c];
                 e = fma(Qc[c] * dlt, dlt, e);
             }
             cost += e;
         }
         if (a.traj && k + 1 == next_save) {
 #pragma unroll
-            for (int c = 0; c < 13; ++c) a.traj[((long)saved * 13 + c) * a.ld + i] = SMEM ? sx[c * ROLLOUT_BLOCK] : x[c];
+            for (int c = 0; c < 13; ++c) a.traj[((long)saved * 13 + c) * a.ld + i] = x[c];
             ++saved; next_save += a.save_every;
         }
-    }
-    if constexpr (SMEM) {
-#pragma unroll
-        for (int c = 0; c < 13; ++c) x[c] = sx[c * ROLLOUT_BLOCK];
     }
 #pragma unroll
     for (int c = 0; c < 13; ++c) a.xf[(long)c * a.ld + i] = x[c];
@@ -673,7 +664,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 }
 constexpr long FP64_PEAK_FMAS_PER_ITER = 64;
 
-// Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic.
+// Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic, 4 asin_sc(x, sqrt(1-x^2)).
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256) k_math_selftest(const double* __restrict__ x, double* __restrict__ out, long n, int which) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,7 +675,8 @@ __global__ void __launch_bounds__(256) k_math_selftest(const double* __restrict_
         case 0: r = fast_rcp(a); break;
         case 1: r = fast_rsqrt(a); break;
         case 2: r = asin_poly(a); break;
-        default: r = fast_logistic(a); break;
+        case 3: r = fast_logistic(a); break;
+        default: { const double c2 = fma(-a, a, 1.0); r = asin_sc(a, c2 > 0.0 ? c2 * fast_rsqrt(c2) : 0.0); } break;
     }
     out[i] = r;
 }

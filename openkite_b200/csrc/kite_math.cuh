@@ -7,7 +7,8 @@
 // produce, drop the denormal/NaN slow paths (non-finite trajectories are flagged by the kernels
 // instead) and share work between related quantities:
 //   rcp / rsqrt : MUFU seed (rcp.approx / rsqrt.approx .ftz.f64) + ONE cubically convergent step
-//   asin        : odd minimax polynomial on |x| <= 0.6 (scripts/fit_math_polys.py), libm fallback outside
+//   asin        : odd minimax polynomial on |x| <= 0.7072 (scripts/fit_math_polys.py), complement identity
+//                 asin(s) = sign(s) (pi/2 - asin(cos)) beyond, so the whole range is branch free
 //   logistic    : exp by Cody-Waite reduction + degree-11 polynomial, then rcp
 // Host builds (tests/cpu_shim) emulate the MUFU seeds with float precision so the same source is
 // checked on the CPU.
@@ -55,25 +56,75 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     return fma(y0, p, y0);
 }
 
-// asin(x) = x + x u P(u), u = x^2, |x| <= ASIN_FAST_MAX; max relative error 2.3e-16 (scripts/fit_math_polys.py)
-#define KITE_ASIN_FAST_MAX 0.6
+// NOTE: the coefficients are written as literals on purpose.  FP64 instructions on sm_100a take constants only through
+// uniform registers; a coefficient TABLE (__constant__ or constexpr array) is hoisted out of the stage loop into
+// ~40 uniform registers, which overflow into vector registers and from there into local memory (228 B of spills
+// in k_rk4_rollout).  Literals are re-materialised next to their use (2 UMOV each) and cost no registers.
+#ifndef KITE_POLY_SPLIT
+#define KITE_POLY_SPLIT 0
+#endif
+
+// asin(x) = x + x u P(u), u = x^2, |x| <= 0.7072; degree 16, max relative error 4.4e-16 (scripts/fit_math_polys.py)
+#define KITE_ASIN_POLY_MAX 0.7072
 __device__ __forceinline__ double asin_poly(double x) {
     const double u = x * x;
-    double p = 7.29997078374671204e-02;
-    p = fma(p, u, -1.04137057612019940e-01);
-    p = fma(p, u, 9.35985258000532616e-02);
-    p = fma(p, u, -3.48182818154024673e-02);
-    p = fma(p, u, 2.18831168546623420e-02);
-    p = fma(p, u, 6.79360522162927773e-03);
-    p = fma(p, u, 1.20052897697550849e-02);
-    p = fma(p, u, 1.39170345012287547e-02);
-    p = fma(p, u, 1.73561602888368215e-02);
-    p = fma(p, u, 2.23720037341655145e-02);
-    p = fma(p, u, 3.03819486815959904e-02);
-    p = fma(p, u, 4.46428570828007673e-02);
-    p = fma(p, u, 7.50000000003340495e-02);
-    p = fma(p, u, 1.66666666666666352e-01);
+#if KITE_POLY_SPLIT
+    // even/odd split in u: two independent Horner chains of half the depth
+    const double u2 = u * u;
+    double pe = 5.27314318387392955e-01, po = -1.67855479930664897e+00;
+    pe = fma(pe, u2, 2.55375757459231778e+00);
+    po = fma(po, u2, -2.35809246022577668e+00);
+    pe = fma(pe, u2, 1.48923001382088138e+00);
+    po = fma(po, u2, -6.56023493249017098e-01);
+    pe = fma(pe, u2, 2.23097241478172448e-01);
+    po = fma(po, u2, -4.34132617562938208e-02);
+    pe = fma(pe, u2, 1.89243203271123074e-02);
+    po = fma(po, u2, 1.03696475274575421e-02);
+    pe = fma(pe, u2, 1.40738595019858897e-02);
+    po = fma(po, u2, 1.73458138976341353e-02);
+    pe = fma(pe, u2, 2.23724499523806075e-02);
+    po = fma(po, u2, 3.03819370896512217e-02);
+    pe = fma(pe, u2, 4.46428572403844703e-02);
+    po = fma(po, u2, 7.49999999994898220e-02);
+    pe = fma(pe, u2, 1.66666666666667102e-01);
+    const double p = fma(po, u, pe);
+#else
+    double p = 5.27314318387392955e-01;
+    p = fma(p, u, -1.67855479930664897e+00);
+    p = fma(p, u, 2.55375757459231778e+00);
+    p = fma(p, u, -2.35809246022577668e+00);
+    p = fma(p, u, 1.48923001382088138e+00);
+    p = fma(p, u, -6.56023493249017098e-01);
+    p = fma(p, u, 2.23097241478172448e-01);
+    p = fma(p, u, -4.34132617562938208e-02);
+    p = fma(p, u, 1.89243203271123074e-02);
+    p = fma(p, u, 1.03696475274575421e-02);
+    p = fma(p, u, 1.40738595019858897e-02);
+    p = fma(p, u, 1.73458138976341353e-02);
+    p = fma(p, u, 2.23724499523806075e-02);
+    p = fma(p, u, 3.03819370896512217e-02);
+    p = fma(p, u, 4.46428572403844703e-02);
+    p = fma(p, u, 7.49999999994898220e-02);
+    p = fma(p, u, 1.66666666666667102e-01);
+#endif
     return fma(x * u, p, x);
+}
+// Angle in [-pi/2, pi/2] from its sine s and cosine c >= 0 (s^2 + c^2 = 1), branch free over the whole range:
+//   |s| <= 1/sqrt2 : asin(s)            |s| > 1/sqrt2 : sign(s) (pi/2 - asin(c)),  c < 1/sqrt2
+// so the polynomial argument never leaves |x| <= 0.7072 and a warp never diverges into libm (random-control
+// rollouts sit at |sideslip| > 37 deg for ~40% of the horizon: profiles/r1f sweep).
+__device__ __forceinline__ double asin_sc(double s, double c) {
+    const bool big = fabs(s) > 0.70710678118654752;
+    const double r = asin_poly(big ? c : s);
+    const double t = (1.5707963267948966 - r) + 6.123233995736766e-17;
+    return big ? copysign(t, s) : r;
+}
+// atan2(y, x) from the normalised pair s = y/hypot, c = x/hypot, any quadrant, branch free:
+//   c >= 0 : asin_sc(s, c)              c < 0 : sign(s) pi - asin_sc(s, -c)
+__device__ __forceinline__ double atan2_sc(double s, double c) {
+    const double r = asin_sc(s, fabs(c));
+    const double t = (copysign(3.141592653589793, s) - r) + copysign(1.2246467991473532e-16, s);
+    return (c < 0.0) ? t : r;
 }
 
 // logistic(x) = 1 / (1 + exp(-x)); argument clamped to +-700 (result 0 / 1 to within 1e-304 beyond).
@@ -86,6 +137,22 @@ __device__ __forceinline__ double fast_logistic(double x) {
     const double nf = tn - magic;
     double r = fma(nf, -6.93146705627441406e-01, a);
     r = fma(nf, -4.74932503903167256e-07, r);
+    // exp(r), |r| <= ln2/2, degree 11 (scripts/fit_math_polys.py)
+#if KITE_POLY_SPLIT
+    const double r2 = r * r;
+    double po = 2.51100492048186583e-08, pe = 2.76326547225277896e-07;
+    po = fma(po, r2, 2.75572408872298695e-06);
+    pe = fma(pe, r2, 2.48014854415613131e-05);
+    po = fma(po, r2, 1.98412698900764028e-04);
+    pe = fma(pe, r2, 1.38888889523528631e-03);
+    po = fma(po, r2, 8.33333333331958900e-03);
+    pe = fma(pe, r2, 4.16666666664879531e-02);
+    po = fma(po, r2, 1.66666666666666796e-01);
+    pe = fma(pe, r2, 5.00000000000001887e-01);
+    po = fma(po, r2, 1.00000000000000000e+00);
+    pe = fma(pe, r2, 1.00000000000000000e+00);
+    const double p = fma(po, r, pe);
+#else
     double p = 2.51100492048186583e-08;
     p = fma(p, r, 2.76326547225277896e-07);
     p = fma(p, r, 2.75572408872298695e-06);
@@ -96,8 +163,9 @@ __device__ __forceinline__ double fast_logistic(double x) {
     p = fma(p, r, 4.16666666664879531e-02);
     p = fma(p, r, 1.66666666666666796e-01);
     p = fma(p, r, 5.00000000000001887e-01);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.00000000000000000e+00);
+    p = fma(p, r, 1.00000000000000000e+00);
+#endif
     // scale by 2^n: n is in the low word of tn (|n| <= 1010, so the biased exponent stays normal)
     int64_t bits;
     memcpy(&bits, &tn, sizeof bits);

@@ -121,14 +121,10 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     const double xe = v[0] + K.eps;
     const double irho = fast_rsqrt(fma(xe, xe, v[2] * v[2]));
     const double ca = xe * irho, sa = v[2] * irho;            // cos/sin(angle of attack)
-    double ss, aoa;
-    if (fabs(sb) <= KITE_ASIN_FAST_MAX && fabs(sa) <= KITE_ASIN_FAST_MAX && xe > 0.0) {
-        ss = asin_poly(sb);                                   // both angles within +-36.8 deg: two interleaved
-        aoa = asin_poly(sa);                                  // polynomial chains, no division, no branches
-    } else {
-        ss = asin(sb);                                        // post-stall / backwards flight: libm, any quadrant
-        aoa = atan2(v[2], xe);
-    }
+    // both angles from their (sin, cos) pairs, branch free for any sideslip and any angle of attack (all four
+    // quadrants): two interleaved polynomial chains, no division, no libm, no warp divergence (kite_math.cuh)
+    const double ss = asin_sc(sb, cb);
+    const double aoa = atan2_sc(sa, ca);
     const double qS = K.cqS * V2;
 
     // ---- aerodynamic force in the wind frame, rotated to body ---------------------------
@@ -508,34 +504,28 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A,
     for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }
 
-// Same step with the state x and the tableau accumulator parked in shared memory ([13][blockDim] columns, conflict
-// free) between stages: only the stage input and the RHS temporaries stay in registers, which buys a fourth
-// resident block per SM (128 instead of 168 registers).  sx/sacc point at this thread's column; stride = blockDim.
+// Variant with only the step base state x parked in shared memory (column of this thread, stride = blockDim): the
+// stage input, the RHS temporaries and the tableau accumulator stay in registers.  Frees 26 registers against rk4_step
+// at the price of 52 LDS + 13 STS per step (~4% of the FP64 instruction count).  On return xt holds the new state.
 template <bool RIGID>
-__device__ __forceinline__ void rk4_step_smem(const KiteConsts& K, const AeroCoef& A, double* __restrict__ sx,
-                                              double* __restrict__ sacc, int stride, const double (&u)[3], double h) {
+__device__ __forceinline__ void rk4_step_xsmem(const KiteConsts& K, const AeroCoef& A, double* __restrict__ sx, int stride,
+                                               double (&xt)[13], const double (&u)[3], double h) {
     NoSink ns;
-    double k[13], xt[13];
+    double k[13], acc[13];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) xt[i] = sx[i * stride];
+    for (int i = 0; i < 13; ++i) { sx[i * stride] = xt[i]; acc[i] = 0.0; }
     const double hh = 0.5 * h;
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
         model_eval<RIGID, false>(K, A, xt, u, k, ns);
         const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
         const double an = (st == 2) ? h : hh;
-        if (st == 0) {
 #pragma unroll
-            for (int i = 0; i < 13; ++i) { sacc[i * stride] = k[i]; xt[i] = fma(an, k[i], sx[i * stride]); }
-        } else if (st < 3) {
-#pragma unroll
-            for (int i = 0; i < 13; ++i) { sacc[i * stride] = fma(wgt, k[i], sacc[i * stride]); xt[i] = fma(an, k[i], sx[i * stride]); }
-        } else {
-            const double h6 = h / 6.0;
-#pragma unroll
-            for (int i = 0; i < 13; ++i) sx[i * stride] = fma(h6, sacc[i * stride] + k[i], sx[i * stride]);
-        }
+        for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], sx[i * stride]); }
     }
+    const double h6 = h / 6.0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) xt[i] = fma(h6, acc[i], sx[i * stride]);
 }
 
 // ---- counter-based synthetic inputs (workload definition; identical to oracle::counter_uniform) ----

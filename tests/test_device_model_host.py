@@ -68,6 +68,23 @@ def test_device_model_vs_oracle_random(shim, prm, oracle):
         assert_close(f, rf[i], 1e-12, what="f"); assert_close(Jx, rJx[i], 1e-11, what="Jx"); assert_close(Ju, rJu[i], 1e-12, what="Ju")
 
 
+def test_device_model_all_quadrants(shim, prm, oracle):
+    """Branch-free angle evaluation (kite_math.cuh asin_sc / atan2_sc): large sideslip, post-stall angles of attack,
+    backwards flight in both rear quadrants, pure sideways / vertical flight, and rest."""
+    x = oracle.synth_x0(0, 12)
+    vs = [[1.0, 0.2, 4.0], [-3.0, 0.1, 0.5], [-3.0, 0.1, -0.5], [2.0, 3.0, 0.1], [2.0, -3.0, 0.1], [0.0, 0.0, 0.0],
+          [0.3, 5.0, 0.2], [1e-3, 0.0, 4.0], [-2.0, 0.0, 0.0], [4.0, 2.9, 2.9], [-1.0, -2.0, -3.0], [5.0, 0.0, -4.9]]
+    for i, v in enumerate(vs):
+        x[i, 0:3] = v
+    u = oracle.synth_controls(0, 12, 1)[:, 0, :]
+    rf = oracle.rhs(x, u); rJx, rJu = oracle.jac(x, u)
+    for i in range(12):
+        f, Jx, Ju = shim_eval(shim, prm, 0, x[i], u[i])
+        assert_close(f, rf[i], 1e-12, what="f[%d]" % i)
+        if i != 5:     # at rest the reference Jacobian itself is 0/0 in places
+            assert_close(Jx, rJx[i], 1e-10, what="Jx[%d]" % i); assert_close(Ju, rJu[i], 1e-12, what="Ju[%d]" % i)
+
+
 def test_device_rk4_config1(shim, prm, golden):
     c = golden["rollout_config1"]
     xn = np.zeros(13)

@@ -316,9 +316,15 @@ def test_lean_math_accuracy(eng):
         got = eng.math_selftest(x, which).cpu().numpy()
         r = ref(x.cpu().numpy())
         assert np.abs(got / r - 1).max() < 1e-15, which
-    xa = torch.from_numpy(rng.uniform(-0.6, 0.6, 200000)).cuda()
+    xa = torch.from_numpy(rng.uniform(-0.7072, 0.7072, 200000)).cuda()
     got = eng.math_selftest(xa, 2).cpu().numpy()
-    assert np.abs(got - np.arcsin(xa.cpu().numpy())).max() < 4e-16
+    assert np.abs(got - np.arcsin(xa.cpu().numpy())).max() < 5e-16
+    # the (sin, cos) pair form covers the whole range branch free; near |x| = 1 the error is that of cos = sqrt(1-x^2)
+    xf = torch.from_numpy(np.concatenate([rng.uniform(-0.999, 0.999, 200000), [0.0, 0.70710678, -0.70710679, 0.9999]])).cuda()
+    got = eng.math_selftest(xf, 4).cpu().numpy()
+    assert np.abs(got - np.arcsin(xf.cpu().numpy())).max() < 1e-14
+    mid = np.abs(xf.cpu().numpy()) < 0.95
+    assert np.abs(got[mid] - np.arcsin(xf.cpu().numpy()[mid])).max() < 1e-15
     xl = torch.from_numpy(np.concatenate([rng.uniform(-60, 60, 200000), [-800.0, 800.0, 0.0]])).cuda()
     got = eng.math_selftest(xl, 3).cpu().numpy()
     xr = xl.cpu().numpy()
@@ -328,7 +334,7 @@ def test_lean_math_accuracy(eng):
 
 
 def test_rollout_post_stall_fallback(eng, okb, oracle):
-    """States outside the fast asin range (|aoa| or |sideslip| > 36.8 deg, backwards flight, v = 0) take the libm path."""
+    """Large angles (|aoa| or |sideslip| beyond 45 deg use the complement form), backwards flight (libm path), v = 0."""
     x0 = oracle.synth_x0(0, 6)
     x0[0, 0:3] = [1.0, 0.2, 4.0]      # aoa ~ 76 deg
     x0[1, 0:3] = [-3.0, 0.1, 0.5]     # flying backwards: aoa in the second quadrant
