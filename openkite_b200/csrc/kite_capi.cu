@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -310,18 +311,20 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
 }
 
 // ---------------------------------------------------------------- sensitivities -------------------
-size_t kite_rk4_sens_work_bytes(long B) { return B > 0 ? sizeof(double) * 4 * (size_t)JAC_SLOTS * (size_t)B : 0; }
+size_t kite_rk4_sens_work_bytes(long B) {
+    if (B <= 0) return 0;
+    // persistent kernel: one private [4][slots][32] region per resident warp, independent of B beyond one wave
+    const long groups = (B + 31) / 32, warps = std::min(groups, sens_fused_max_warps());
+    return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP_MAX * (size_t)warps;
+}
 
 static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, const double* x, const double* u, double* xn,
                           double* Phi, double* Gamma, void* work) {
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     SensArgs a{ctx->K, B, ld, h, x, u, xn, Phi, Gamma, (double*)work};
-    // scratch uses its own leading dimension == B (ldw); kernels index scratch with a.ld, so ld must equal ldw
     (void)ldw;
-    launch_sens_stage_jac(a, rigid, ctx->stream);
-    LAUNCH_CHECK("k_sens_stage_jac");
-    launch_sens_propagate(a, rigid, ctx->K.has_arm != 0, ctx->stream);
-    LAUNCH_CHECK("k_sens_propagate");
+    launch_sens_fused(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    LAUNCH_CHECK("k_sens_fused");
     return KITE_OK;
 }
 

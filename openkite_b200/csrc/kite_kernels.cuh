@@ -9,6 +9,7 @@
 // =====================================================================================
 #pragma once
 #include <cuda_pipeline.h>
+#include <cuda/annotated_ptr>
 
 #include "kite_model.cuh"
 
@@ -226,10 +227,19 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 }
 
 // ================================================================================================
-// RK4 step sensitivities, two kernels.
-//   A: thread per unit   -- primal RK4 stages + analytic stage Jacobians -> compact scratch Jw[4][132][ld]
-//   B: 16 lanes per unit -- lane c owns tangent column c of [Phi | Gamma]; S_i = J_i' + a_i h Jx_i S_{i-1}
-//      chained through the tableau with S in registers; stage Jacobian entries are broadcast loads.
+// RK4 step sensitivities: one persistent kernel, every warp independent (no CTA barrier anywhere).
+//   A warp owns groups of 32 units.  Per group:
+//   phase A (lane = unit):  primal RK4 stages + analytic stage Jacobians, written to the warp's PRIVATE scratch
+//                           Jw[warp][stage][slot][32 units] in global memory.  The region (4 x 111 x 256 B = 114 KB per
+//                           warp, 135 MB for 148 x 8 warps) is rewritten every group and read back within microseconds,
+//                           so it is served from the 126 MB L2 instead of making the 3.5 KB/unit round trip through HBM
+//                           that bounded the earlier two-kernel version (profiles/r1e: HBM-write bound at 5.9 TB/s).
+//   phase B (8 lanes = unit, 4 units per pass, 8 passes): lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] and runs
+//                           the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers (E = seed [I | 0; 0 | I]).
+//                           The stage tile of the pass ([slot][4 units], 3.5 KB, contiguous in the scratch) is brought
+//                           L2 -> shared by ONE bulk copy (TMA, cp.async.bulk + mbarrier) per tile into a warp-private
+//                           4-deep ring, read back as conflict-free broadcast LDS with immediate offsets, and
+//                           [Phi | Gamma] leaves straight from registers as full 32 B sectors (4 consecutive units per row).
 // ================================================================================================
 struct SensArgs {
     KiteConsts K;
@@ -237,192 +247,221 @@ struct SensArgs {
     double h;
     const double* x; const double* u;
     double* xn; double* Phi; double* Gamma;
-    double* Jw;     // [4][JAC_SLOTS][ld]
+    double* Jw;     // scratch: [resident warp][4 stages][8 passes][slots][4 units]
 };
 
-template <bool RIGID>
-__global__ void __launch_bounds__(128) k_sens_stage_jac(const __grid_constant__ SensArgs a) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.B) return;
-    double x[13], u[3], k[13], acc[13], xt[13];
-#pragma unroll
-    for (int c = 0; c < 13; ++c) { x[c] = __ldg(a.x + (long)c * a.ld + i); xt[c] = x[c]; acc[c] = 0.0; }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) u[c] = __ldg(a.u + (long)c * a.ld + i);
-    const double hh = 0.5 * a.h;
-    const long stage_stride = (long)JAC_SLOTS * a.ld;
-    // stage loop kept rolled: one copy of the f + Jacobian code in the instruction stream (the 4x unrolled body
-    // stalled on instruction fetch: no_instruction 1.34 per issue in profiles/r1a)
-#pragma unroll 1
-    for (int st = 0; st < 4; ++st) {
-        CompactSink s{a.Jw + st * stage_stride + i, a.ld};
-        model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, s);
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-        const double an = (st == 2) ? a.h : hh;
-#pragma unroll
-        for (int c = 0; c < 13; ++c) { acc[c] = fma(wgt, k[c], acc[c]); xt[c] = fma(an, k[c], x[c]); }
-    }
-    const double h6 = a.h / 6.0;
-#pragma unroll
-    for (int c = 0; c < 13; ++c) a.xn[(long)c * a.ld + i] = fma(h6, acc[c], x[c]);
-}
+#ifndef KITE_SF_WARPS
+#define KITE_SF_WARPS 6                        // measured 5..8 on B200 (profiles/r1m): 6 warps = 101 MB of scratch stay L2 resident
+#endif
+constexpr int SF_WARPS = KITE_SF_WARPS;        // warps per CTA (one CTA per SM): scratch footprint = SMs x warps x 114 KB
+constexpr int SF_RING = 4;                     // stage tiles in flight per warp
+template <bool ARM> struct SfCfg {
+    static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;      // slots a stage Jacobian occupies
+    static constexpr int TILE = NS * 4;                               // doubles per tile: [slot][4 units], contiguous in scratch
+    static constexpr int TILE_S = TILE + 4;                           // shared-memory tile: + one zero row (gather target)
+    static constexpr unsigned TILE_BYTES = TILE * 8;                  // one bulk copy (multiple of 16)
+    static constexpr long SCRATCH_PER_WARP = 4L * 8 * TILE;           // doubles: [stage][pass][slot][4]
+    // dynamic shared memory: ring tiles | phase-A columns x[13][32], acc[13][32], u[3][32] per warp | mbarriers
+    static constexpr size_t SMEM_RING = sizeof(double) * SF_WARPS * SF_RING * TILE_S;
+    static constexpr size_t SMEM_XA = sizeof(double) * SF_WARPS * 29 * 32;
+    static constexpr size_t SMEM = SMEM_RING + SMEM_XA + sizeof(unsigned long long) * SF_WARPS * SF_RING;
+};
+constexpr long SF_SCRATCH_PER_WARP_MAX = 4L * 8 * JAC_SLOTS * 4;
 
-// ---- kernel B: tangent propagation ---------------------------------------------------------------------
-// CTA = 256 threads = 32 units x 8 lanes; lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] (13 state seeds,
-// 3 control seeds).  Per stage the unit's compact Jacobian is staged global -> shared with cp.async (coalesced
-// 256 B rows, double buffered against the previous stage's FMAs), transposed to tile[unit][slot] so that the 8 lanes
-// of a unit read it back as broadcast LDS.128 (two entries per load, 1 load per 4 DFMA).  S, S_next and the tableau
-// accumulator (3 x 13 x 2 doubles) live in registers; results leave through shared memory as coalesced 256 B rows.
-constexpr int SENS_UNITS = 32;                 // units per CTA
-constexpr int SENS_TS = 133;                   // tile row stride in doubles: odd => the 32 units of a fill row and the 4 units of a
-                                               // broadcast read land in distinct banks (profiles/r1c: stride 134 had 4-way conflicts)
-constexpr int SENS_OS = 33;                    // output staging row stride (padded)
-constexpr int SENS_THREADS = 256;
-
-constexpr int SENS_RING = 4;                   // stage tiles in flight (cp.async ring): the next batch streams in behind the FMAs
-
-struct SensSmem {
-    double tile[SENS_RING][SENS_UNITS * SENS_TS];   // ring of stage Jacobian tiles [unit][slot]
-    double out[208 * SENS_OS];                      // output staging [component row][unit]
+// L2 residency hints: the scratch is tagged evict_last (persisting) when written and when read back, everything that
+// streams through once (inputs, xn, Phi, Gamma) is evict_first, so the streaming output does not push the scratch out.
+typedef cuda::annotated_ptr<double, cuda::access_property::persisting> PersistPtr;
+struct WarpSink {       // compact slots of this lane's unit: [pass = lane / 4][slot][lane % 4]
+    PersistPtr base;    // &Jw[stage][lane / 4][0][lane % 4]: a warp store fills 8 whole 32-byte sectors
+    __device__ __forceinline__ void jx(int i, int j, double v) { base[jx_slot(i, j) * 4] = v; }
+    __device__ __forceinline__ void ju(int i, int j, double v) { base[ju_slot(i, j) * 4] = v; }
 };
 
-template <bool ARM, bool RIGID>
-__device__ __forceinline__ void sens_fill_tile(double* __restrict__ tile, const double* __restrict__ Jst, long ld, long unit0,
-                                               long B, int tid) {
-    constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;
-    const int u = tid & 31;
-    if (unit0 + u < B) {
-        const double* src = Jst + unit0 + u;
-        double* dst = tile + u * SENS_TS;
-#pragma unroll 4
-        for (int sl = tid >> 5; sl < NS; sl += SENS_THREADS / 32) __pipeline_memcpy_async(dst + sl, src + (long)sl * ld, 8);
-    }
+// ---- mbarrier / bulk-copy (TMA) helpers, single-CTA scope --------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (one instruction, no per-lane work), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s_evict_last(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
-// Persistent CTA: loops over batches of 32 units; tile t = batch * 4 + stage.  Tiles t+1..t+3 are always in flight.
 template <bool ARM, bool RIGID>
-__global__ void __launch_bounds__(SENS_THREADS, 1) k_sens_propagate(const __grid_constant__ SensArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SensSmem& sm = *reinterpret_cast<SensSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lu = tid >> 3;                       // unit within the batch (8 consecutive lanes share a unit)
-    const int l = tid & 7;
-    const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane
-    const long stage_stride = (long)JAC_SLOTS * a.ld;
-    const long nbatch = (a.B + SENS_UNITS - 1) / SENS_UNITS;
-    const long my_batches = (nbatch > blockIdx.x) ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long ntiles = my_batches * 4;
-    auto issue = [&](long t) {                     // tile t of this CTA -> ring slot t % RING (always commits a group)
-        if (t < ntiles) {
-            const long batch = blockIdx.x + (t >> 2) * gridDim.x;
-            sens_fill_tile<ARM, RIGID>(sm.tile[t % SENS_RING], a.Jw + (t & 3) * stage_stride, a.ld, batch * SENS_UNITS, a.B, tid);
-        }
-        __pipeline_commit();
-    };
-    // pad slot (index JAC_SLOTS of every tile row) reads as 0.0: structural zeros of a Jacobian column point at it
-    for (int t = tid; t < SENS_RING * SENS_UNITS; t += SENS_THREADS) sm.tile[t / SENS_UNITS][(t % SENS_UNITS) * SENS_TS + JAC_SLOTS] = 0.0;
-    for (int t = 0; t < SENS_RING - 1; ++t) issue(t);
-    // per-lane slot indices of Jacobian columns c0, c1 (13 rows each), one byte per row packed into registers:
-    // stage 1 has D = E, so S_1 = [Jx | Ju] E is a pure gather of two columns -- no FMAs, 26 loads instead of 111
+__global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_constant__ SensArgs a) {
+    using C = SfCfg<ARM>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* const ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * SF_RING * C::TILE_S;
+    double* const sxa = reinterpret_cast<double*>(smem_raw + C::SMEM_RING) + (size_t)warp * 29 * 32 + lane;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_RING + C::SMEM_XA) + warp * SF_RING;
+    const long gw = (long)blockIdx.x * SF_WARPS + warp, nwarps = (long)gridDim.x * SF_WARPS;
+    double* const Jw = a.Jw + gw * C::SCRATCH_PER_WARP;
+    const long ngroups = (a.B + 31) / 32;
+    const int lu = lane >> 3, l = lane & 7;
+    const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane in phase B
+
+    // zero row of every ring tile (structural zeros of a gathered Jacobian column point at it) and the warp's mbarriers
+    if (lane < 4 * SF_RING) ring[(lane >> 2) * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
+    if (lane < SF_RING) mbar_init(bars + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    // per-lane slot indices of Jacobian columns c0, c1 (13 rows each), one byte per row; NS = the zero row
     unsigned pk0[4] = {0, 0, 0, 0}, pk1[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         int s0 = SLOT_TAB.col[i][c0], s1 = SLOT_TAB.col[i][c1];
-        if (s0 < 0 || (!ARM && s0 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c0 >= 13))) s0 = JAC_SLOTS;
-        if (s1 < 0 || (!ARM && s1 >= JAC_SLOTS_NOARM) || (RIGID && (i < 6 || c1 >= 13))) s1 = JAC_SLOTS;
+        if (s0 < 0 || s0 >= C::NS || (RIGID && (i < 6 || c0 >= 13))) s0 = C::NS;
+        if (s1 < 0 || s1 >= C::NS || (RIGID && (i < 6 || c1 >= 13))) s1 = C::NS;
         pk0[i >> 2] |= (unsigned)s0 << (8 * (i & 3));
         pk1[i >> 2] |= (unsigned)s1 << (8 * (i & 3));
     }
+    const double h6 = a.h / 6.0, hh = 0.5 * a.h;
+    // tile t = pass * 4 + stage of the current group -> ring slot t % 4 = stage: ONE bulk copy of 3.5 KB issued by lane 0
+    auto issue = [&](int t) {
+        if (lane == 0 && t < 32) {
+            const int st = t & 3;
+            mbar_expect_tx(bars + st, C::TILE_BYTES);
+            bulk_g2s_evict_last(ring + st * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES, bars + st);
+        }
+    };
+    // inputs of a group -> the warp's shared columns x[13][32] (rows 0..12) and u[3][32] (rows 26..28), asynchronously
+    auto prefetch_inputs = [&](long g) {
+        if (g < ngroups) {
+            const long unit = g * 32 + lane;
+            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last unit, store nothing
+#pragma unroll
+            for (int c = 0; c < 13; ++c) __pipeline_memcpy_async(sxa + c * 32, a.x + (long)c * a.ld + ui, 8);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __pipeline_memcpy_async(sxa + (26 + c) * 32, a.u + (long)c * a.ld + ui, 8);
+        }
+        __pipeline_commit();
+    };
+    prefetch_inputs(gw);
 
-    // Stage recursion in "input tangent" form, which is uniform across lanes (no per-lane gather of Jacobian columns):
-    //   D_i = E + a_i h S_{i-1}   (E = seed matrix [I | 0]),   S_i = Jx_i D_i + Ju_i Eu   (Eu = [0 | I]),
-    //   [Phi | Gamma] = E + h/6 (S_1 + 2 S_2 + 2 S_3 + S_4).
-    // Each lane carries columns c0, c1 of D/S and of the accumulator; Jacobian entries are broadcast LDS.
-    double D0[13], D1[13], N0[13], N1[13], A0[13], A1[13];
-    double U0[3], U1[3];
+    for (long g = gw; g < ngroups; g += nwarps) {
+        // ---------------- phase A: lane = unit --------------------------------------------------------------
+        {
+            const long unit = g * 32 + lane;
+            // the step base state and the tableau accumulator are parked in shared memory ([13][32] columns): the
+            // Jacobian code needs every register (profiles/r1j: spill loads on the critical path were 60% of phase A)
+            double u[3], k[13], xt[13];
+            __pipeline_wait_prior(0);                   // this lane's inputs (prefetched during the previous phase B)
 #pragma unroll
-    for (int m = 0; m < 3; ++m) { U0[m] = (13 + m == c0) ? 1.0 : 0.0; U1[m] = (13 + m == c1) ? 1.0 : 0.0; }
-    const double h6 = a.h / 6.0;
+            for (int c = 0; c < 13; ++c) xt[c] = sxa[c * 32];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = sxa[(26 + c) * 32];
+#pragma unroll 1
+            for (int st = 0; st < 4; ++st) {
+                WarpSink sink{PersistPtr(Jw + ((long)st * 8 + (lane >> 2)) * C::TILE + (lane & 3))};
+                model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
+                const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+                const double an = (st == 2) ? a.h : hh;
+#pragma unroll
+                for (int c = 0; c < 13; ++c) {
+                    sxa[(13 + c) * 32] = (st == 0) ? k[c] : fma(wgt, k[c], sxa[(13 + c) * 32]);
+                    xt[c] = fma(an, k[c], sxa[c * 32]);
+                }
+            }
+            if (unit < a.B) {
+#pragma unroll
+                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, sxa[(13 + c) * 32], sxa[c * 32]));
+            }
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores above -> async-proxy (bulk copy) reads below
+        __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
+        prefetch_inputs(g + nwarps);                    // next group's x, u land in shared memory behind phase B
 
-    for (long bi = 0; bi < my_batches; ++bi) {
-        const long unit0 = (blockIdx.x + bi * gridDim.x) * SENS_UNITS;
+        // ---------------- phase B: 8 lanes = unit, 4 units per pass -------------------------------------------
+#pragma unroll 1
+        for (int t = 0; t < SF_RING - 1; ++t) issue(t);
+        double D[2][16], N0[13], N1[13], A0[13], A1[13];   // D[.][13..15]: the control part of the seed (constant)
 #pragma unroll
-        for (int j = 0; j < 13; ++j) { D0[j] = (j == c0) ? 1.0 : 0.0; D1[j] = (j == c1) ? 1.0 : 0.0; }
+        for (int m = 13; m < 16; ++m) { D[0][m] = (m == c0) ? 1.0 : 0.0; D[1][m] = (m == c1) ? 1.0 : 0.0; }
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const long unit = g * 32 + p * 4 + lu;
+            const unsigned par = p & 1;                 // each ring slot completes once per pass, 8 (even) times per group
+            // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
+            __syncwarp();                               // all lanes are past the previous tile: its ring slot is free
+            issue(p * 4 + SF_RING - 1);
+            mbar_wait(bars + 0, par);
+            {
+                const double* __restrict__ T = ring + lu;
+                // keep the packed indices opaque so that the 26 unpacked offsets are not hoisted into registers
 #pragma unroll
-        for (int st = 0; st < 4; ++st) {
-            const long t = bi * 4 + st;
-            __pipeline_wait_prior(SENS_RING - 2);  // tile t landed (t+1, t+2 may still be in flight)
-            __syncthreads();                       // ... and is visible; everyone is past tile t-1, so its ring slot is free
-            issue(t + SENS_RING - 1);
-            const double* __restrict__ T = sm.tile[t % SENS_RING] + lu * SENS_TS;
-            if (st == 0) {
+                for (int w = 0; w < 4; ++w) asm volatile("" : "+r"(pk0[w]), "+r"(pk1[w]));
 #pragma unroll
                 for (int i = 0; i < 13; ++i) {
-                    N0[i] = T[(pk0[i >> 2] >> (8 * (i & 3))) & 0xffu];
-                    N1[i] = T[(pk1[i >> 2] >> (8 * (i & 3))) & 0xffu];
+                    N0[i] = T[((pk0[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
+                    N1[i] = T[((pk1[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
                 }
-            } else {
-                // column-major traversal of the sparse Jacobian: for each input row j the (up to 13) entries J[i][j]
-                // update 26 independent accumulator chains N[i][c], so consecutive DFMAs never depend on each other
+#pragma unroll
+                for (int i = 0; i < 13; ++i) {
+                    A0[i] = N0[i]; A1[i] = N1[i];
+                    D[0][i] = fma(hh, N0[i], (i == c0) ? 1.0 : 0.0);
+                    D[1][i] = fma(hh, N1[i], (i == c1) ? 1.0 : 0.0);
+                }
+            }
+            // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled: instruction-cache footprint)
+#pragma unroll 1
+            for (int st = 1; st < 4; ++st) {
+                __syncwarp();
+                issue(p * 4 + st + SF_RING - 1);
+                mbar_wait(bars + st, par);
+                const double* __restrict__ T = ring + st * C::TILE_S + lu;   // ring slot = (4 p + st) % 4 = st
 #pragma unroll
                 for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
+                // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
+                // N[i][.], so consecutive DFMAs never depend on each other; columns 13..15 are the control seed
 #pragma unroll
-                for (int j = 0; j < 13; ++j) {
+                for (int j = 0; j < 16; ++j) {
 #pragma unroll
                     for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
-                        if (jx_nz(i, j, ARM)) {
-                            const double jv = T[jx_slot(i, j)];   // broadcast LDS.64 (4 distinct addresses per warp)
-                            N0[i] = fma(jv, D0[j], N0[i]);
-                            N1[i] = fma(jv, D1[j], N1[i]);
+                        if ((j < 13) ? jx_nz(i, j, ARM) : (!RIGID && ju_nz(i, j - 13))) {
+                            const double jv = T[SLOT_TAB.col[i][j] * 4];     // broadcast LDS.64, immediate offset
+                            N0[i] = fma(jv, D[0][j], N0[i]);
+                            N1[i] = fma(jv, D[1][j], N1[i]);
                         }
                     }
                 }
-                if (!RIGID) {
+                const double wgt = (st == 3) ? 1.0 : 2.0;
+                const double an = (st == 2) ? a.h : hh;
 #pragma unroll
-                    for (int m = 0; m < 3; ++m) {
-#pragma unroll
-                        for (int i = 0; i < 13; ++i) {
-                            if (ju_nz(i, m)) {
-                                const double jv = T[ju_slot(i, m)];
-                                N0[i] = fma(jv, U0[m], N0[i]);
-                                N1[i] = fma(jv, U1[m], N1[i]);
-                            }
-                        }
-                    }
+                for (int i = 0; i < 13; ++i) {
+                    A0[i] = fma(wgt, N0[i], A0[i]);
+                    A1[i] = fma(wgt, N1[i], A1[i]);
+                    D[0][i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);   // unused after the last stage
+                    D[1][i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
                 }
             }
-            const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-            const double an = (st == 2) ? a.h : 0.5 * a.h;        // a_{i+1} h, applied after stage i
+            if (unit < a.B) {
+                // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
+                double* const o0 = (c0 < 13) ? a.Phi + (long)c0 * a.ld + unit : a.Gamma + (long)(c0 - 13) * a.ld + unit;
+                double* const o1 = (c1 < 13) ? a.Phi + (long)c1 * a.ld + unit : a.Gamma + (long)(c1 - 13) * a.ld + unit;
+                const long r0 = (c0 < 13 ? 13 : 3) * a.ld, r1 = (c1 < 13 ? 13 : 3) * a.ld;
 #pragma unroll
-            for (int i = 0; i < 13; ++i) {
-                A0[i] = (st == 0) ? N0[i] : fma(wgt, N0[i], A0[i]);
-                A1[i] = (st == 0) ? N1[i] : fma(wgt, N1[i], A1[i]);
-                if (st < 3) {
-                    D0[i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);
-                    D1[i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                for (int i = 0; i < 13; ++i) {
+                    __stcs(o0 + i * r0, fma(h6, A0[i], (i == c0) ? 1.0 : 0.0));
+                    __stcs(o1 + i * r1, fma(h6, A1[i], (i == c1) ? 1.0 : 0.0));
                 }
             }
         }
-        // results -> shared [row r = component][unit] (padded rows) -> coalesced 256 B rows
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            const double v0 = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
-            const double v1 = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
-            const int r0 = (c0 < 13) ? (i * 13 + c0) : (169 + i * 3 + (c0 - 13));
-            const int r1 = (c1 < 13) ? (i * 13 + c1) : (169 + i * 3 + (c1 - 13));
-            sm.out[r0 * SENS_OS + lu] = v0;
-            sm.out[r1 * SENS_OS + lu] = v1;
-        }
-        __syncthreads();
-        const int u = tid & 31;
-        if (unit0 + u < a.B) {
-            for (int r = tid >> 5; r < 208; r += SENS_THREADS / 32) {
-                const double v = sm.out[r * SENS_OS + u];
-                if (r < 169) a.Phi[(long)r * a.ld + unit0 + u] = v;
-                else a.Gamma[(long)(r - 169) * a.ld + unit0 + u] = v;
-            }
-        }
-        // the next iteration's first __syncthreads orders these reads of sm.out before it is overwritten again
+        __syncwarp();                                   // every lane is done reading the ring before the next group
     }
     __pipeline_wait_prior(0);
 }

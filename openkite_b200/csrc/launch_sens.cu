@@ -1,25 +1,31 @@
 #include "kite_launch.h"
 namespace kite {
-void launch_sens_stage_jac(const SensArgs& a, bool rigid, cudaStream_t s) {
-    if (rigid) k_sens_stage_jac<true><<<blocks_for(a.B, 128), 128, 0, s>>>(a);
-    else k_sens_stage_jac<false><<<blocks_for(a.B, 128), 128, 0, s>>>(a);
-}
 template <bool ARM, bool RIGID>
-static void go_propagate(const SensArgs& a, cudaStream_t s) {
+static void go_fused(const SensArgs& a, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_sens_propagate<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SensSmem));
+        cudaFuncSetAttribute(k_sens_fused<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
         configured = true;
     }
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const unsigned nb = blocks_for(a.B, SENS_UNITS);
-    const unsigned grid = nb < (unsigned)sms ? nb : (unsigned)sms;      // persistent: one CTA per SM
-    k_sens_propagate<ARM, RIGID><<<grid, SENS_THREADS, sizeof(SensSmem), s>>>(a);
+    const long ngroups = (a.B + 31) / 32;
+    const long want = (ngroups + SF_WARPS - 1) / SF_WARPS;
+    const long sms = sens_fused_max_warps() / SF_WARPS;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
+    k_sens_fused<ARM, RIGID><<<grid, SF_WARPS * 32, SfCfg<ARM>::SMEM, s>>>(a);
 }
-void launch_sens_propagate(const SensArgs& a, bool rigid, bool arm, cudaStream_t s) {
-    if (rigid) go_propagate<false, true>(a, s);
-    else if (arm) go_propagate<true, false>(a, s);
-    else go_propagate<false, false>(a, s);
+long sens_fused_max_warps() {
+    static long warps = 0;
+    if (!warps) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            return 256L * SF_WARPS;                                     // no device visible: a safe upper bound for sizing
+        warps = (long)sms * SF_WARPS;
+    }
+    return warps;
+}
+void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, cudaStream_t s) {
+    if (rigid) go_fused<false, true>(a, s);
+    else if (arm) go_fused<true, false>(a, s);
+    else go_fused<false, false>(a, s);
 }
 }  // namespace kite

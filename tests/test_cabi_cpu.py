@@ -66,6 +66,12 @@ def test_no_cpu_fallback(lib, yaml_path):
 
 
 def test_work_size_queries(lib):
-    assert lib.kite_rk4_sens_work_bytes(10) == 8 * 4 * 132 * 10
+    # fused sensitivity kernel: one private [4 stages][132 slots][32 units] region per resident warp, one warp per
+    # 32 units, capped at the number of warps the persistent grid runs (device dependent; 256 SMs x 8 without a device)
+    per_warp = 8 * 4 * 132 * 32
+    assert lib.kite_rk4_sens_work_bytes(10) == per_warp
+    assert lib.kite_rk4_sens_work_bytes(33) == 2 * per_warp
+    big = lib.kite_rk4_sens_work_bytes(1 << 24)
+    assert big % per_warp == 0 and 8 <= big // per_warp <= 256 * 8
     assert lib.kite_ekf_work_bytes(10) == 8 * 132 * 10
     assert lib.kite_rk4_sens_work_bytes(0) == 0
