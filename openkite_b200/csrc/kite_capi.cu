@@ -371,8 +371,6 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
     CK(cudaSetDevice(ctx->device));
     if (ctx->small.reserve(sizeof(double) * (size_t)M * M + 4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemcpyAsync(ctx->small.ptr, compD_h, sizeof(double) * (size_t)M * M, cudaMemcpyHostToDevice, ctx->stream));
-    if (JX_d) CK(cudaMemsetAsync(JX_d, 0, sizeof(double) * (size_t)M * 225 * (size_t)ld, ctx->stream));
-    if (JU_d) CK(cudaMemsetAsync(JU_d, 0, sizeof(double) * (size_t)M * 60 * (size_t)ld, ctx->stream));
     CollocArgs a{};
     a.K = ctx->K; a.B = B; a.ld = ld; a.M = M; a.tau = tau;
     for (int i = 0; i < 15; ++i) { a.sx[i] = sx_h[i]; a.isx[i] = 1.0 / sx_h[i]; }

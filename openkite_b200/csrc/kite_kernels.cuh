@@ -648,6 +648,27 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             // augmented rows: theta_dot = V1 (x[14]), V1_dot = u_v (u[3])   (kiteNMPF.cpp:62-73)
             if (a.JX) sink.jxp[(long)(13 * 15 + 14) * a.ld] = a.sx[13] * a.isx[14];
             if (a.JU) sink.jup[(long)(14 * 4 + 3) * a.ld] = a.sx[14] * a.isu[3];
+            // structural zeros of the dense node blocks are written here, once, instead of a memset pass over the
+            // 25 KB/scenario output beforehand (the kernel is HBM-write bound: every byte is stored exactly once)
+            if (a.JX) {
+                const bool arm = a.K.has_arm != 0;
+#pragma unroll
+                for (int i = 0; i < 15; ++i)
+#pragma unroll
+                    for (int j = 0; j < 15; ++j) {
+                        const bool kite_blk = (i < 13 && j < 13);
+                        const bool nz_noarm = kite_blk ? jx_nz(i, j, false) : (i == 13 && j == 14);
+                        const bool nz_arm = kite_blk ? jx_nz(i, j, true) : (i == 13 && j == 14);
+                        if (!nz_arm || (!nz_noarm && !arm)) sink.jxp[(long)(i * 15 + j) * a.ld] = 0.0;
+                    }
+            }
+            if (a.JU) {
+#pragma unroll
+                for (int i = 0; i < 15; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (!((i < 13 && j < 3) ? ju_nz(i, j) : (i == 14 && j == 3))) sink.jup[(long)(i * 4 + j) * a.ld] = 0.0;
+            }
             double fa[15];
 #pragma unroll
             for (int c = 0; c < 13; ++c) fa[c] = a.sx[c] * f[c];
