@@ -162,7 +162,7 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
 /* ---------------------------------------------------------------- EKF -------------------- */
 /* Replaces: KiteEKF::propagate (kiteEKF.cpp:75-98): xn = RK4(x,u,dt); A = I + Jx(x,u) dt; Pn = A P A^T + W.
  *   x_d [13][ld], u_d [3][ld], P_d [169][ld], W_h HOST 13x13 row-major; xn_d, Pn_d like x_d, P_d.
- *   work_d: device scratch of kite_ekf_work_bytes(B) bytes. */
+ *   work_d: device scratch of kite_ekf_work_bytes(B) bytes (currently 0: the Jacobian stays in shared memory; may be NULL). */
 size_t kite_ekf_work_bytes(long B);
 int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const double* x_d, const double* u_d,
                            const double* P_d, const double* W_h, double* xn_d, double* Pn_d, void* work_d);

@@ -383,14 +383,14 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
 }
 
 // ---------------------------------------------------------------- EKF -----------------------------
-size_t kite_ekf_work_bytes(long B) { return B > 0 ? sizeof(double) * (size_t)JAC_SLOTS * (size_t)B : 0; }
+size_t kite_ekf_work_bytes(long) { return 0; }      // the predict kernel keeps the Jacobian in shared memory
 
 int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const double* x_d, const double* u_d,
                            const double* P_d, const double* W_h, double* xn_d, double* Pn_d, void* work_d) {
     if (ctx && B == 0) return KITE_OK;
-    if (!ctx || B < 0 || ld < B || !x_d || !P_d || !W_h || !xn_d || !Pn_d || !work_d)
+    (void)work_d;
+    if (!ctx || B < 0 || ld < B || !x_d || !P_d || !W_h || !xn_d || !Pn_d)
         return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: bad argument");
-    if (ld != B) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: ld must equal B");
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     if (!rigid && !u_d) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: u_d is null");
     if (P_d == Pn_d) return fail(ctx, KITE_ERR_ARG, "kite_ekf_predict_batch: P_d and Pn_d must not alias");
@@ -398,11 +398,9 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     CK(cudaSetDevice(ctx->device));
     if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemcpyAsync(ctx->small.ptr, W_h, sizeof(double) * 169, cudaMemcpyHostToDevice, ctx->stream));
-    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (double*)work_d, (const double*)ctx->small.ptr};
-    launch_ekf_state_jac(a, rigid, ctx->stream);
-    LAUNCH_CHECK("k_ekf_state_jac");
-    launch_ekf_cov(a, rigid, ctx->K.has_arm != 0, ctx->stream);
-    LAUNCH_CHECK("k_ekf_cov");
+    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr};
+    launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    LAUNCH_CHECK("k_ekf_predict");
     return KITE_OK;
 }
 

@@ -55,13 +55,6 @@ static_assert(make_slot_tab().jx[12][12] == 103, "slot numbering");
 static_assert(make_slot_tab().ju[5][2] == JAC_SLOTS_NOARM - 1, "slot numbering");
 static_assert(make_slot_tab().jx[5][12] == JAC_SLOTS - 1, "slot numbering");
 
-// Sink: compact slots, SoA over units.
-struct CompactSink {
-    double* base;   // &J[0*ld + unit]
-    long ld;
-    __device__ __forceinline__ void jx(int i, int j, double v) const { base[(long)jx_slot(i, j) * ld] = v; }
-    __device__ __forceinline__ void ju(int i, int j, double v) const { base[(long)ju_slot(i, j) * ld] = v; }
-};
 // Sink: dense 13x13 / 13x3 row-major, SoA over units (buffers pre-zeroed by the caller).
 struct DenseSink {
     double* jxp; double* jup; long ld;
@@ -467,10 +460,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
 }
 
 // ================================================================================================
-// EKF predict (kiteEKF.cpp:75-98), two kernels.
-//   A: thread per filter   -- xn = RK4(x,u,dt) and Jx(x,u) at the PRE-step state -> compact scratch
-//   B: 16 lanes per filter -- Q = P A^T (lane j owns row j), transposed through shared memory,
-//                             Pn = A Q + W (lane j owns column j); A = I + dt Jx, sparse broadcast loads.
+// EKF predict (kiteEKF.cpp:75-98): xn = RK4(x,u,dt); A = I + dt Jx(x,u) at the PRE-step state; Pn = A P A^T + W.
+// One persistent kernel, every warp independent; the Jacobian never leaves the SM.
+//   phase A (lane = filter, 32 filters per group): analytic Jacobian at the pre-step state -> the warp's shared tile
+//            Jt[pass = lane / 4][slot][lane % 4], then the RK4 step -> xn.
+//   phase B (8 lanes = filter, 4 filters per pass): lane l owns rows {2l, 2l+1} of P (lanes 0..6; 13 rows):
+//            Q = P A^T  (row r: q = p + dt J p), transposed through a small shared buffer, then Pn = A Q + W
+//            (column c: q + dt J q + W[:, c]).  Jacobian entries are conflict-free broadcast LDS with immediate offsets.
 // ================================================================================================
 struct EkfArgs {
     KiteConsts K;
@@ -478,65 +474,127 @@ struct EkfArgs {
     double dt;
     const double* x; const double* u; const double* P;
     double* xn; double* Pn;
-    double* Jw;              // [JAC_SLOTS][ld]
     const double* W;         // device [169]
 };
+template <bool ARM> struct EfCfg {
+    static constexpr int WARPS = ARM ? 5 : 6;                         // shared memory bound: 35 / 40 KB per warp
+    static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;
+    // pass stride == 4 (mod 16) doubles: the 8 four-lane groups of a phase-A store land in distinct bank octets
+    static constexpr int PS = NS * 4 + ((NS * 4) % 16 == 12 ? 8 : ((NS * 4) % 16 == 0 ? 4 : (20 - (NS * 4) % 16) % 16));
+    static constexpr int QR = 15;                                     // transpose buffer row stride (odd: conflict-free rows)
+    static constexpr int QS = 4 * 13 * QR;                            // transpose buffer [4 filters][13][QR]
+    static constexpr int PER_WARP = 8 * PS + QS + 172;                // doubles (+ W, 13 x 13, padded)
+    static constexpr size_t SMEM = sizeof(double) * WARPS * PER_WARP;
+};
+static_assert(EfCfg<false>::PS % 16 == 4 && EfCfg<true>::PS % 16 == 4, "bank-conflict-free pass stride");
 
-template <bool RIGID>
-__global__ void __launch_bounds__(128) k_ekf_state_jac(const __grid_constant__ EkfArgs a) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.B) return;
-    double x[13], u[3], f[13];
+struct SmemSink {       // compact slots of this lane's filter in the warp's shared tile
+    double* base;       // &Jt[lane / 4][0][lane % 4]
+    __device__ __forceinline__ void jx(int i, int j, double v) const { base[jx_slot(i, j) * 4] = v; }
+    __device__ __forceinline__ void ju(int, int, double) const {}     // the EKF uses the state Jacobian only
+};
+
+// y[i] += sum_j J[i][j] v[j] for two vectors at once, J from the shared tile column of this lane's filter
+template <bool ARM, bool RIGID>
+__device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, const double (&v0)[13], const double (&v1)[13],
+                                              double (&y0)[13], double (&y1)[13]) {
 #pragma unroll
-    for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x + (long)c * a.ld + i);
+    for (int i = 0; i < 13; ++i) { y0[i] = 0.0; y1[i] = 0.0; }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldg(a.u + (long)c * a.ld + i) : 0.0;
-    {
-        CompactSink s{a.Jw + i, a.ld};
-        model_eval<RIGID, true>(a.K, a.K.A, x, u, f, s);
+    for (int j = 0; j < 13; ++j) {
+#pragma unroll
+        for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
+            if (jx_nz(i, j, ARM)) {
+                const double jv = T[jx_slot(i, j) * 4];
+                y0[i] = fma(jv, v0[j], y0[i]);
+                y1[i] = fma(jv, v1[j], y1[i]);
+            }
+        }
     }
-    rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
-#pragma unroll
-    for (int c = 0; c < 13; ++c) a.xn[(long)c * a.ld + i] = x[c];
 }
 
 template <bool ARM, bool RIGID>
-__global__ void __launch_bounds__(256) k_ekf_cov(const __grid_constant__ EkfArgs a) {
-    __shared__ double tile[16][13][14];            // [unit in CTA][row][col], padded
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long unit = t >> 4;
-    const int j = (int)(t & 15);
-    const int lu = (int)(threadIdx.x >> 4);
-    const bool active = (unit < a.B) && (j < 13);
-    const double* __restrict__ J = a.Jw + (unit < a.B ? unit : 0);
-    double pr[13], q[13];
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < 13; ++k) pr[k] = __ldg(a.P + (long)(j * 13 + k) * a.ld + unit);   // row j of P
-        // q = A pr = pr + dt Jx pr    (row j of Q = P A^T)
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 13; ++k)
-                if (jx_nz(i, k, ARM) && !(RIGID && i < 6)) s = fma(__ldg(J + (long)jx_slot(i, k) * a.ld), pr[k], s);
-            q[i] = fma(a.dt, s, pr[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 13; ++i) tile[lu][j][i] = q[i];
-    }
+__global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const __grid_constant__ EkfArgs a) {
+    using C = EfCfg<ARM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* const Jt = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::PER_WARP;
+    double* const Qt = Jt + 8 * C::PS;
+    double* const Ws = Qt + C::QS;                 // the warp's copy of W (13 x 13 row-major)
+    const long gw = (long)blockIdx.x * C::WARPS + warp, nwarps = (long)gridDim.x * C::WARPS;
+    const long ngroups = (a.B + 31) / 32;
+    const int lu = lane >> 3, l = lane & 7;
+    const int r0 = 2 * l, r1 = 2 * l + 1;          // rows of P (phase B, first product) = columns of Pn (second product)
+    const bool v0 = r0 < 13, v1 = r1 < 13;
+    for (int t = lane; t < 169; t += 32) Ws[t] = __ldg(a.W + t);
     __syncwarp();
-    if (active) {
+    // rows r0, r1 of P for the 4 filters of a pass (registers; issued one pass ahead so the loads fly behind the FMAs)
+    auto load_rows = [&](long g, int p, double (&q0)[13], double (&q1)[13]) {
+        const long unit = g * 32 + p * 4 + lu;
+        const long ui = unit < a.B ? unit : a.B - 1;
 #pragma unroll
-        for (int k = 0; k < 13; ++k) pr[k] = tile[lu][k][j];      // column j of Q
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 13; ++k)
-                if (jx_nz(i, k, ARM) && !(RIGID && i < 6)) s = fma(__ldg(J + (long)jx_slot(i, k) * a.ld), pr[k], s);
-            a.Pn[(long)(i * 13 + j) * a.ld + unit] = fma(a.dt, s, pr[i]) + __ldg(a.W + i * 13 + j);
+        for (int k = 0; k < 13; ++k) {
+            q0[k] = v0 ? __ldcs(a.P + (long)(r0 * 13 + k) * a.ld + ui) : 0.0;
+            q1[k] = v1 ? __ldcs(a.P + (long)(r1 * 13 + k) * a.ld + ui) : 0.0;
         }
+    };
+
+    for (long g = gw; g < ngroups; g += nwarps) {
+        double pn0[13], pn1[13];
+        load_rows(g, 0, pn0, pn1);                  // first pass's rows of P land behind phase A
+        // ---------------- phase A: lane = filter ------------------------------------------------------------
+        {
+            const long unit = g * 32 + lane;
+            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
+            double x[13], u[3], f[13];
+#pragma unroll
+            for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
+            {
+                SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
+                model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
+            }
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
+            if (unit < a.B) {
+#pragma unroll
+                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B: 8 lanes = filter, 4 filters per pass -------------------------------------
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const long unit = g * 32 + p * 4 + lu;
+            const double* __restrict__ T = Jt + p * C::PS + lu;
+            double* const Q = Qt + lu * (13 * C::QR);
+            double p0[13], p1[13], n0[13], n1[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) { p0[k] = pn0[k]; p1[k] = pn1[k]; }
+            if (p < 7) load_rows(g, p + 1, pn0, pn1);
+            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+            __syncwarp();                               // the previous pass is done reading the transpose buffer
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {              // rows r0, r1 of Q = P A^T
+                if (v0) Q[r0 * C::QR + k] = fma(a.dt, n0[k], p0[k]);
+                if (v1) Q[r1 * C::QR + k] = fma(a.dt, n1[k], p1[k]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {              // columns r0, r1 of Q
+                p0[k] = v0 ? Q[k * C::QR + r0] : 0.0;
+                p1[k] = v1 ? Q[k * C::QR + r1] : 0.0;
+            }
+            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+            if (unit < a.B) {
+#pragma unroll
+                for (int i = 0; i < 13; ++i) {          // columns r0, r1 of Pn = A Q + W
+                    if (v0) __stcs(a.Pn + (long)(i * 13 + r0) * a.ld + unit, fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0]);
+                    if (v1) __stcs(a.Pn + (long)(i * 13 + r1) * a.ld + unit, fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1]);
+                }
+            }
+        }
+        __syncwarp();                                   // phase B is done with the Jacobian tile before the next group
     }
 }
 

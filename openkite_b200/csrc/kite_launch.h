@@ -9,8 +9,7 @@ void launch_rollout_23(const RolloutArgs& a, int umode, bool rigid, bool percoef
 void launch_synth_inputs(const SynthArgs& a, cudaStream_t s);
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, cudaStream_t s);
 long sens_fused_max_warps();   // warps of the persistent fused kernel on the current device (scratch sizing)
-void launch_ekf_state_jac(const EkfArgs& a, bool rigid, cudaStream_t s);
-void launch_ekf_cov(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
+void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
 void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s);
 void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s);
