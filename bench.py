@@ -22,9 +22,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # Algorithmic FP64 flops per unit of work: own op-counting oracle for the plain step
-# (oracle.flop_counts(): 1888; SURVEY.md 8d survey count 1909), SURVEY.md 8d figure for RK4 + sensitivities.
+# (oracle.flop_counts(): 1888; SURVEY.md 8d survey count 1909), SURVEY.md 8d figures for the other kernels.
 FLOPS_RK4_STEP = 1888.0
 FLOPS_RK4_SENS_STEP = 27800.0
+FLOPS_EKF_PREDICT = 13400.0
+BYTES_COLLOC_SCENARIO = 8.0 * (209 + 165 + 11 * 285)      # z in, G + dense node blocks out (HBM-write bound kernel)
+BYTES_EKF_FILTER = 8.0 * (13 + 3 + 169 + 13 + 169)
 FP64_NOMINAL_TFLOPS = 37.2     # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz
 METRIC = "batched kite RK4 state-steps/sec"
 UNIT = "state-steps/s"
@@ -41,7 +44,7 @@ def parse():
     ap.add_argument("--h", type=float, default=1e-3)
     ap.add_argument("--e2e-traj", type=int, default=0, help="trajectories for the host-buffer e2e leg (0 = same as --traj)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sens", action="store_true")
+    ap.add_argument("--no-sens", action="store_true", help="skip the secondary kernels (sensitivities, EKF predict, collocation)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -143,9 +146,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    from openkite_b200.sharding import shard_range
+
     B, N, h = args.traj, args.horizon, args.h
     eng = okb.Engine(okb.load_properties(os.path.join(ROOT, "data", "umx_radian.yaml")), okb.KITE, device=local)
-    index0 = rank * B
+    index0, count = shard_range(world * B, world, rank)       # weak scaling: every rank owns B trajectories
+    assert count == B
     x0, u = eng.synth_inputs(B, N, index0=index0)           # inputs resident in HBM: x0 [13,B], u [N,3,B] (~25 GB)
     xf = eng.empty(13, B)
     gathered = eng.empty(world * 13 * B) if world > 1 else None
@@ -192,11 +198,28 @@ def main():
 
     # ---- roofline of the dominant kernel (k_rk4_rollout): FP64 FMA pipe ---------------------------
     achieved_tflops = FLOPS_RK4_STEP * B * N / (kernel_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    try:     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from a committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as fh:
+            for row in json.load(fh)["captures"]:
+                if row["trajectories"] == B and row["rk4_steps"] == N:
+                    traffic, traffic_src = row["dram_bytes_per_launch"], row["source"]
+    except Exception:
+        pass
+    hbm_peak = 6555.8
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm_peak = float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        pass
+    hbm_gbs = (24.0 * B * N + 208.0 * B) / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "fp64_fma", "kernel": "k_rk4_rollout<U_PER_STEP>", "achieved": achieved_tflops, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "peak_source": "measured here (kite_fp64_peak DFMA microbenchmark); "
                 "MEASURED_PEAKS.json has no FP64 entry", "frac_of_nominal_37.2": achieved_tflops / FP64_NOMINAL_TFLOPS,
                 "flops_per_state_step": FLOPS_RK4_STEP, "kernel_ms": kernel_ms,
-                "hbm_gbs_controls": 24.0 * B * N / (kernel_ms * 1e-3) / 1e9, "traffic": None}
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 24.0 * B * N + 208.0 * B,
+                "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                        "note": "not the bound: 79 flop per byte of control stream"}}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -207,32 +230,53 @@ def main():
                       "sharding": "contiguous blocks of trajectories per rank, global index = rank*B + i"},
            "roofline": roofline, "clocks": clocks, "gpu_launches": launches}
 
-    # ---- secondary: RK4 + forward sensitivities (config 3 shape, B units per launch pair) ------------
+    # ---- secondary kernels (rank 0): RK4 + sensitivities (config 3), EKF predict (config 5), collocation (config 4) ----
     if not args.no_sens and rank == 0:
+        def timed(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
         Bs = min(B, 1 << 20)
         xs, us = x0[:, :Bs].contiguous(), u[0, :, :Bs].contiguous()
         outs = (eng.empty(13, Bs), eng.empty(169, Bs), eng.empty(39, Bs))
-        w = eng.workspace(eng.L.kite_rk4_sens_work_bytes(Bs))
-        import ctypes as C
-        pp = lambda t_: C.c_void_p(t_.data_ptr())
-        def sens():
-            eng._use_torch_stream()
-            eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, Bs, Bs, 0.02, pp(xs), pp(us), pp(outs[0]), pp(outs[1]), pp(outs[2]), pp(w)))
-        for _ in range(3):
-            sens()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        a.record()
-        for _ in range(reps):
-            sens()
-        b.record(); torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / reps
+        ms = timed(lambda: eng.sens_step(xs, us, 0.02, out=outs), 10)
         tf = FLOPS_RK4_SENS_STEP * Bs / (ms * 1e-3) / 1e12
-        out["rk4_sens"] = {"units": Bs, "ms": ms, "state_steps_per_s": Bs / (ms * 1e-3), "achieved_tflops": tf,
+        out["rk4_sens"] = {"kernel": "k_sens_fused", "units": Bs, "ms": ms, "state_steps_per_s": Bs / (ms * 1e-3), "achieved_tflops": tf,
                            "frac_of_measured_peak": tf / fp64_peak, "flops_per_unit": FLOPS_RK4_SENS_STEP,
                            "hbm_gbs_out": (169 + 39 + 13) * 8.0 * Bs / (ms * 1e-3) / 1e9}
-        del outs, xs, us
+        import numpy as np
+        Wd = np.diag(np.array([.5, .5, .5, .5, .5, .5, .5, .1, .1, .01, .05, .05, .05]) ** 2)     # kiteEKF.cpp:6-13
+        Pe = torch.from_numpy((10 * Wd).reshape(169, 1)).to(dev).expand(169, Bs).contiguous()
+        eo = (outs[0], outs[1])
+        ms = timed(lambda: eng.ekf_predict(xs, us, 0.0084, Pe, Wd, out=eo), 5)
+        tf = FLOPS_EKF_PREDICT * Bs / (ms * 1e-3) / 1e12
+        out["ekf_predict"] = {"kernel": "k_ekf_predict", "units": Bs, "ms": ms, "filters_per_s": Bs / (ms * 1e-3), "achieved_tflops": tf,
+                              "frac_of_measured_peak": tf / fp64_peak, "hbm_gbs": BYTES_EKF_FILTER * Bs / (ms * 1e-3) / 1e9}
+        del outs, eo, Pe
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as fh:
+                cg = json.load(fh)["cases"]["colloc_nmpc_P5_S2_scaled"]
+            Bc, M = 65536, 11
+            zc = (torch.tensor(cg["z"], dtype=torch.float64, device=dev).reshape(209, 1)
+                  * (1 + 0.01 * torch.randn(209, Bc, dtype=torch.float64, device=dev))).contiguous()
+            from openkite_b200.collocation import comp_diff_matrix
+            compD = comp_diff_matrix(5, 2)
+            co = (eng.empty(M * 15, Bc), eng.empty(M * 225, Bc), eng.empty(M * 60, Bc), eng.empty(Bc))
+            ms = timed(lambda: eng.colloc_eval(zc, M, compD, 0.25, cg["sx"], cg["su"], out=co), 5)
+            gbs = BYTES_COLLOC_SCENARIO * Bc / (ms * 1e-3) / 1e9
+            out["colloc_eval"] = {"kernel": "k_colloc_eval", "scenarios": Bc, "ms": ms, "scenarios_per_s": Bc / (ms * 1e-3),
+                                  "bound": "hbm", "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak}
+            del co, zc
+        except Exception as e:      # secondary figure only
+            out["colloc_eval"] = {"error": str(e)}
+        del xs, us
 
     # ---- e2e: same metric through the C ABI with HOST buffers (H2D of inputs, D2H of results in the timed region)
     if not args.no_e2e:

@@ -215,10 +215,10 @@ class Engine:
         return x0, u
 
     # ---- sensitivities -------------------------------------------------------------------------
-    def sens_step(self, x, u, h):
+    def sens_step(self, x, u, h, out=None):
         self._use_torch_stream()
         B = x.shape[1]
-        xn, Phi, Gam = self.empty(13, B), self.empty(169, B), self.empty(39, B)
+        xn, Phi, Gam = out if out is not None else (self.empty(13, B), self.empty(169, B), self.empty(39, B))
         w = self.workspace(self.L.kite_rk4_sens_work_bytes(B))
         self._ck(self.L.kite_rk4_sens_step(self.ctx, B, B, h, _ptr(x), _ptr(u), _ptr(xn), _ptr(Phi), _ptr(Gam), _ptr(w)))
         return xn, Phi, Gam

@@ -173,3 +173,14 @@ def test_counter_rng_is_sharding_invariant(oracle):
     assert a[..., 0].min() >= 0 and a[..., 0].max() <= 0.3
     x0 = oracle.synth_x0(0, 16)
     assert np.abs(np.linalg.norm(x0[:, 9:13], axis=1) - 1).max() < 1e-15
+
+
+def test_python_collocation_operators_match_oracle(oracle):
+    """openkite_b200/collocation.py (product-side host helper) against the oracle's operators and closed forms."""
+    from openkite_b200.collocation import colloc_points, comp_diff_matrix, diff_matrix, quad_weights
+    for P, S in ((5, 2), (2, 3), (10, 1), (4, 3)):
+        assert_close(colloc_points(P), oracle.cheb_points(P), 1e-15, what="points")
+        assert_close(diff_matrix(P), oracle.cheb_diff(P), 1e-13, what="D")
+        assert_close(quad_weights(P), np.ravel(oracle.cheb_weights(P)), 1e-13, what="weights")
+        assert_close(comp_diff_matrix(P, S), oracle.cheb_compdiff(P, S), 1e-13, what="compD")
+    assert abs(diff_matrix(5)[0, 0] - 8.5) < 1e-13 and abs(quad_weights(5).sum() - 2.0) < 1e-14
