@@ -159,6 +159,23 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
                      const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
                      double* gnorm_d);
 
+/* NMPC performance index and its gradient for B scenarios.
+ * Replaces: Chebyshev<SX,P,S,15,4,0>::CollocateCost (chebyshev.hpp:280-333) applied to the Lagrange and Mayer terms
+ * of KiteNMPF::createNLP (kiteNMPF.cpp:116-143) -- the NLP objective "f" IPOPT evaluates every iteration:
+ *   residual = Sx[6:9] path(x[13] / Sx[13]) - x[6:9],  L = sum Q residual^2 + W (vref - x[14])^2 + sum R u^2,
+ *   cost = Mayer(X_0) + sum_segments tau sum_m w_m L(X_{seg P + m}, U_{seg P + m}),  Mayer = sum Q residual^2.
+ * The path is a circle of path_radius / path_altitude rotated by the unit quaternion path_q, which is how both callers
+ * of the reference build it (nmpf_node.cpp:31-39, kite_control_test.cpp:242-247).
+ *   qw_h [P+1] HOST Clenshaw-Curtis weights (Chebyshev::QWeights), tau = (tf-t0)/(2S), sx_h[15] HOST state scaling
+ *   z_d [M*15 + M*4][ld] (M = S*P+1, same layout as kite_colloc_eval), cost_d [ld], grad_d [M*19][ld] or NULL. */
+typedef struct kite_nmpc_cost {
+    double Q[3], R[4], W;                 /* kiteNMPF.cpp:32-34: Q = 1e2 diag(10,10,100), R = diag(1e-4,1e-1,1e-1,1e-3), W = 1e-3 */
+    double vref_scaled;                   /* Scale_X(14,14) * vel_ref (kiteNMPF.h:34) */
+    double path_radius, path_altitude, path_q[4];
+} kite_nmpc_cost;
+int kite_colloc_cost(kite_ctx* ctx, long B, long ld, int P, int S, const double* qw_h, double tau, const double* sx_h,
+                     const kite_nmpc_cost* cost, const double* z_d, double* cost_d, double* grad_d);
+
 /* ---------------------------------------------------------------- EKF -------------------- */
 /* Replaces: KiteEKF::propagate (kiteEKF.cpp:75-98): xn = RK4(x,u,dt); A = I + Jx(x,u) dt; Pn = A P A^T + W.
  *   x_d [13][ld], u_d [3][ld], P_d [169][ld], W_h HOST 13x13 row-major; xn_d, Pn_d like x_d, P_d.

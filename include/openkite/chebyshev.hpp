@@ -97,6 +97,61 @@ public:
         return std::make_shared<Collocated>(kite.context(), _CompDiff, t_scale, ScaleX, ScaleU);
     }
 
+    /** Collocated performance index of the path-following NMPC (chebyshev.hpp:280-333 applied to the Lagrange and Mayer
+     *  terms of kiteNMPF.cpp:116-143).  The reference takes the two terms as casadi::Function objects; here they are
+     *  described by their parameters (weights, scaled reference velocity, circular path) and evaluated on the GPU. */
+    class CollocatedCost {
+    public:
+        CollocatedCost(std::shared_ptr<KiteContext> ctx, const DM& qw, double tau, const DM& Sx, const kite_nmpc_cost& c)
+            : Ctx(ctx), tau_(tau), cost_(c) {
+            for (int i = 0; i <= PolyOrder; ++i) qw_[i] = qw.size1() > 1 ? qw[i] : qw(0, i);
+            for (int i = 0; i < 15; ++i) sx[i] = Sx.size2() > 1 ? Sx(i, i) : Sx[i];
+            if (kite_device_malloc((void**)&buf, sizeof(double) * ((size_t)NODES * 38 + 1)) != 0) throw std::runtime_error("CollocatedCost: device allocation failed");
+        }
+        ~CollocatedCost() { if (buf) kite_device_free(buf); }
+        CollocatedCost(const CollocatedCost&) = delete;
+        /** performance_idx(z), as PerformanceIndex / nlp_f (kiteNMPF.cpp:143,152) */
+        double operator()(const DM& z) { DM g; return eval(z, g, false); }
+        /** value and gradient with respect to z = [X ; U] */
+        double eval(const DM& z, DM& grad, bool want_grad = true) {
+            const int M = NODES;
+            if (z.numel() != M * 19) throw std::invalid_argument("CollocatedCost::eval: z must have NODES*(15+4) elements");
+            double* z_d = buf; double* g_d = z_d + M * 19; double* c_d = g_d + M * 19;
+            Ctx->h2d(z_d, z.ptr(), (size_t)M * 19);
+            Ctx->check(kite_colloc_cost(Ctx->ctx, 1, 1, PolyOrder, NumSegments, qw_, tau_, sx, &cost_, z_d, c_d, want_grad ? g_d : nullptr), "kite_colloc_cost");
+            double c = 0.0;
+            Ctx->d2h(&c, c_d, 1);
+            if (want_grad) { grad = DM(M * 19, 1); Ctx->d2h(grad.ptr(), g_d, (size_t)M * 19); }
+            return c;
+        }
+        /** batched device entry point: see kite_colloc_cost in include/kite_b200.h */
+        void eval_device(long B, const double* z_d, double* cost_d, double* grad_d) {
+            Ctx->check(kite_colloc_cost(Ctx->ctx, B, B, PolyOrder, NumSegments, qw_, tau_, sx, &cost_, z_d, cost_d, grad_d), "kite_colloc_cost");
+        }
+
+    private:
+        std::shared_ptr<KiteContext> Ctx;
+        double tau_;
+        kite_nmpc_cost cost_;
+        double qw_[PolyOrder + 1], sx[15];
+        double* buf = nullptr;
+    };
+    std::shared_ptr<CollocatedCost> CollocateCost(KiteDynamics& kite, const kite_nmpc_cost& terms, const DM& ScaleX, const double& t0, const double& tf) {
+        static_assert(NX == 15 && NU == 4 && NP == 0, "the GPU cost evaluator implements the NMPC's augmented kite model (15 states, 4 controls)");
+        return std::make_shared<CollocatedCost>(kite.context(), _QuadWeights, (tf - t0) / (2 * NumSegments), ScaleX, terms);
+    }
+    /** Lagrange / Mayer weights and reference velocity with the defaults of KiteNMPF (kiteNMPF.cpp:32-34,42-43; kiteNMPF.h:34). */
+    static kite_nmpc_cost DefaultCost(const DM& ScaleX, double vel_ref, double radius, double altitude, const DM& q_rot) {
+        kite_nmpc_cost c;
+        c.Q[0] = 1e2 * 1e1; c.Q[1] = 1e2 * 1e1; c.Q[2] = 1e2 * 1e2;
+        c.R[0] = 1e-4; c.R[1] = 1e-1; c.R[2] = 1e-1; c.R[3] = 1e-3;
+        c.W = 1e-3;
+        c.vref_scaled = (ScaleX.size2() > 1 ? ScaleX(14, 14) : ScaleX[14]) * vel_ref;
+        c.path_radius = radius; c.path_altitude = altitude;
+        for (int i = 0; i < 4; ++i) c.path_q[i] = q_rot[i];
+        return c;
+    }
+
 private:
     /** Chebyshev-Gauss-Lobatto points x_k = cos(k pi / P) (chebyshev.hpp:119-127); index 0 is the FINAL time. */
     static DM CollocPoints() { DM X(PolyOrder + 1, 1); for (int k = 0; k <= PolyOrder; ++k) X[k] = std::cos(k * (M_PI / PolyOrder)); return X; }

@@ -8,5 +8,5 @@ Product layout:
   collocation.py  host-side Chebyshev operators (constant matrices handed to kite_colloc_eval)
 The C++ host mirror of the reference API (KiteDynamics, ODESolver, KiteEKF, Chebyshev) lives in include/openkite/.
 """
-from .engine import (Engine, KiteError, KiteParams, load_properties, load_library, KITE, KITE_ID, RIGID_BODY,  # noqa: F401
+from .engine import (Engine, KiteError, KiteParams, NmpcCost, load_properties, load_library, KITE, KITE_ID, RIGID_BODY,  # noqa: F401
                      U_CONST, U_PER_STEP, U_SHARED, U_SYNTH, LIB_PATH)

@@ -79,6 +79,7 @@ struct kite_ctx {
     DevBuf scratch;                      // ekf update out-of-place P
     DevBuf pipe[2];                      // host-pipeline chunk buffers
     DevBuf shared_u, shared_y;
+    DevBuf node_w;                       // collocated-cost node weights
     nccl_comm_t comm = nullptr;
     int nranks = 1, rank = 0;
 };
@@ -119,7 +120,7 @@ int kite_destroy(kite_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
     ctx->small.release(); ctx->scratch.release(); ctx->pipe[0].release(); ctx->pipe[1].release();
-    ctx->shared_u.release(); ctx->shared_y.release();
+    ctx->shared_u.release(); ctx->shared_y.release(); ctx->node_w.release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
@@ -379,6 +380,42 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
     a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d;
     launch_colloc_eval(a, p_d != nullptr, ctx->stream);
     LAUNCH_CHECK("k_colloc_eval");
+    return KITE_OK;
+}
+
+int kite_colloc_cost(kite_ctx* ctx, long B, long ld, int P, int S, const double* qw_h, double tau, const double* sx_h,
+                     const kite_nmpc_cost* c, const double* z_d, double* cost_d, double* grad_d) {
+    if (ctx && B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || P < 1 || S < 1 || S * P + 1 > 1024 || !qw_h || !sx_h || !c || !z_d || !cost_d)
+        return fail(ctx, KITE_ERR_ARG, "kite_colloc_cost: bad argument");
+    const int M = S * P + 1;
+    CK(cudaSetDevice(ctx->device));
+    // node weights: node seg*P + m carries tau * w_m; a node shared by two segments carries both (chebyshev.hpp:298-330)
+    std::vector<double> wnode((size_t)M, 0.0);
+    for (int k = 0; k < S; ++k)
+        for (int m = 0; m <= P; ++m) wnode[(size_t)k * P + m] += tau * qw_h[m];
+    if (ctx->node_w.reserve(sizeof(double) * 1024)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    double* wd = (double*)ctx->node_w.ptr;
+    CK(cudaMemcpyAsync(wd, wnode.data(), sizeof(double) * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+    CostArgs a{};
+    a.B = B; a.ld = ld; a.M = M;
+    for (int i = 0; i < 3; ++i) { a.sx6[i] = sx_h[6 + i]; a.Q[i] = c->Q[i]; }
+    a.sx13 = sx_h[13]; a.isx13 = 1.0 / sx_h[13];
+    for (int i = 0; i < 4; ++i) a.R[i] = c->R[i];
+    a.W = c->W; a.vref = c->vref_scaled;
+    // path = vec( conj(q) (x) [0, P] (x) q ) = M(q)^T P with P = [r cos, r sin, alt]
+    const double s0 = c->path_q[0], v1 = c->path_q[1], v2 = c->path_q[2], v3 = c->path_q[3];
+    const double Mq[3][3] = {{s0 * s0 + v1 * v1 - v2 * v2 - v3 * v3, 2 * (v1 * v2 - s0 * v3), 2 * (v1 * v3 + s0 * v2)},
+                             {2 * (v1 * v2 + s0 * v3), s0 * s0 - v1 * v1 + v2 * v2 - v3 * v3, 2 * (v2 * v3 - s0 * v1)},
+                             {2 * (v1 * v3 - s0 * v2), 2 * (v2 * v3 + s0 * v1), s0 * s0 - v1 * v1 - v2 * v2 + v3 * v3}};
+    for (int i = 0; i < 3; ++i) {
+        a.rc[i] = Mq[0][i] * c->path_radius;
+        a.rs[i] = Mq[1][i] * c->path_radius;
+        a.ra[i] = Mq[2][i] * c->path_altitude;
+    }
+    a.wnode = wd; a.z = z_d; a.cost = cost_d; a.grad = grad_d;
+    launch_colloc_cost(a, ctx->stream);
+    LAUNCH_CHECK("k_colloc_cost");
     return KITE_OK;
 }
 

@@ -125,10 +125,18 @@ struct RolloutArgs {
     long index0;
 };
 
-constexpr int ROLLOUT_BLOCK = 128;
+#ifndef KITE_ROLLOUT_BLOCK
+#define KITE_ROLLOUT_BLOCK 128
+#endif
+constexpr int ROLLOUT_BLOCK = KITE_ROLLOUT_BLOCK;
+#ifdef KITE_ROLLOUT_MAXNREG          // experiments: cap registers directly (occupancy between the launch-bounds steps)
+#define KITE_ROLLOUT_ATTR __maxnreg__(KITE_ROLLOUT_MAXNREG)
+#else
+#define KITE_ROLLOUT_ATTR __launch_bounds__(ROLLOUT_BLOCK, 3)
+#endif
 
 template <int UMODE, bool RIGID, bool PERCOEF, bool SMEM>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK, 3) k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
+__global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
     // SMEM: the step base state is parked in shared memory during the four stages (rk4_step_xsmem), [13][block] columns
     __shared__ double sh[SMEM ? 13 * ROLLOUT_BLOCK : 1];
     double* const sx = sh + threadIdx.x;
@@ -761,6 +769,86 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             for (int l = 0; l < NPB; ++l) t += red[l][lane];
             a.gnorm[s] = t;
         }
+    }
+}
+
+// ================================================================================================
+// NMPC performance index and gradient (Chebyshev::CollocateCost chebyshev.hpp:280-333 on the Lagrange / Mayer terms of
+// kiteNMPF.cpp:116-143).  Thread (scenario, node): reads the 9 components of z the cost depends on, writes the 19
+// gradient entries of its node (structural zeros included, so every output byte is stored exactly once) and adds its
+// weighted Lagrange value to the scenario's cost through shared memory.  HBM bound: 72 B in, 152 B out per node.
+// ================================================================================================
+struct CostArgs {
+    long B, ld;
+    int M;
+    double sx6[3], isx13, sx13;         // Scale_X entries used by the cost
+    double Q[3], R[4], W, vref;         // weights, scaled reference velocity
+    double rc[3], rs[3], ra[3];         // path(theta) = rc cos(theta) + rs sin(theta) + ra  (radius, altitude, rotation folded)
+    const double* wnode;                // device [M]: tau * (sum of the quadrature weights of the segments a node belongs to)
+    const double* z; double* cost; double* grad;
+};
+template <int NPB>
+__global__ void __launch_bounds__(32 * NPB) k_colloc_cost(const __grid_constant__ CostArgs a) {
+    __shared__ double red[NPB][32];
+    const int lane = threadIdx.x, ky = threadIdx.y;
+    const long s = (long)blockIdx.x * 32 + lane;
+    const int M = a.M;
+    double acc = 0.0;
+    if (s < a.B) {
+        for (int k = ky; k < M; k += NPB) {
+            const double* zx = a.z + (long)(k * 15) * a.ld + s;
+            const double* zu = a.z + (long)(M * 15 + k * 4) * a.ld + s;
+            double xr[3], us[4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xr[c] = __ldg(zx + (long)(6 + c) * a.ld);
+            const double x13 = __ldg(zx + 13L * a.ld), x14 = __ldg(zx + 14L * a.ld);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) us[c] = __ldg(zu + (long)c * a.ld);
+            double sn, cs;
+            sincos(a.isx13 * x13, &sn, &cs);
+            double pc = 0.0, dth = 0.0, gr[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double pp = fma(a.rc[c], cs, fma(a.rs[c], sn, a.ra[c]));
+                const double dpp = fma(a.rs[c], cs, -a.rc[c] * sn);
+                const double r = fma(a.sx6[c], pp, -xr[c]);
+                const double qr = a.Q[c] * r;
+                pc = fma(qr, r, pc);
+                gr[c] = -2.0 * qr;
+                dth = fma(2.0 * qr * a.sx6[c], dpp, dth);
+            }
+            dth *= a.isx13;
+            const double dv = a.vref - x14;
+            double L = fma(a.W * dv, dv, pc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) L = fma(a.R[c] * us[c], us[c], L);
+            const double w = __ldg(a.wnode + k);
+            const double wm = (k == 0) ? w + 1.0 : w;          // Mayer term sits on node 0 (the final time) with weight 1
+            acc = fma(w, L, acc);
+            if (k == 0) acc += pc;
+            if (a.grad) {
+                double* gx = a.grad + (long)(k * 15) * a.ld + s;
+                double* gu = a.grad + (long)(M * 15 + k * 4) * a.ld + s;
+#pragma unroll
+                for (int c = 0; c < 15; ++c) {
+                    double v = 0.0;
+                    if (c >= 6 && c < 9) v = wm * gr[c - 6];
+                    else if (c == 13) v = wm * dth;
+                    else if (c == 14) v = -2.0 * w * a.W * dv;
+                    gx[(long)c * a.ld] = v;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) gu[(long)c * a.ld] = 2.0 * w * a.R[c] * us[c];
+            }
+        }
+    }
+    red[ky][lane] = acc;
+    __syncthreads();
+    if (ky == 0 && s < a.B) {
+        double t = 0.0;
+#pragma unroll
+        for (int l = 0; l < NPB; ++l) t += red[l][lane];
+        a.cost[s] = t;
     }
 }
 

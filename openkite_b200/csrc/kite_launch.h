@@ -12,6 +12,7 @@ long sens_fused_max_warps();   // warps of the persistent fused kernel on the cu
 void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
 void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s);
+void launch_colloc_cost(const CostArgs& a, cudaStream_t s);
 void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s);
 void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s);
 inline unsigned blocks_for(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }

@@ -9,4 +9,8 @@ void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s) {
     if (percoef) k_colloc_eval<true, KITE_COLLOC_NPB><<<gb, block, 0, s>>>(a);
     else k_colloc_eval<false, KITE_COLLOC_NPB><<<gb, block, 0, s>>>(a);
 }
+void launch_colloc_cost(const CostArgs& a, cudaStream_t s) {
+    dim3 block(32, 4);
+    k_colloc_cost<4><<<blocks_for(a.B, 32), block, 0, s>>>(a);
+}
 }  // namespace kite

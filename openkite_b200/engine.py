@@ -54,6 +54,21 @@ def load_properties(path):
     return p
 
 
+class NmpcCost(C.Structure):
+    """Mirror of `struct kite_nmpc_cost` (include/kite_b200.h); defaults of kiteNMPF.cpp:32-34."""
+    _fields_ = [("Q", C.c_double * 3), ("R", C.c_double * 4), ("W", C.c_double), ("vref_scaled", C.c_double),
+                ("path_radius", C.c_double), ("path_altitude", C.c_double), ("path_q", C.c_double * 4)]
+
+    @classmethod
+    def defaults(cls, sx, vel_ref=0.05, radius=2.65, altitude=0.0, q_rot=(1.0, 0.0, 0.0, 0.0)):
+        c = cls()
+        c.Q[:] = [1e3, 1e3, 1e4]; c.R[:] = [1e-4, 1e-1, 1e-1, 1e-3]; c.W = 1e-3
+        c.vref_scaled = float(sx[14]) * vel_ref
+        c.path_radius, c.path_altitude = radius, altitude
+        c.path_q[:] = list(q_rot)
+        return c
+
+
 class KiteError(RuntimeError):
     pass
 
@@ -86,6 +101,7 @@ def load_library():
     L.kite_rk4_sens_step.argtypes = [vp, lg, lg, db, dp, dp, dp, dp, dp, dp]
     L.kite_rk4_sens_rollout.argtypes = [vp, lg, lg, lg, db, dp, dp, dp, dp, dp, dp]
     L.kite_colloc_eval.argtypes = [vp, lg, lg, ip, dp, db, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.kite_colloc_cost.argtypes = [vp, lg, lg, ip, ip, dp, db, dp, C.POINTER(NmpcCost), dp, dp, dp]
     L.kite_ekf_work_bytes.argtypes = [lg]; L.kite_ekf_work_bytes.restype = C.c_size_t
     L.kite_ekf_predict_batch.argtypes = [vp, lg, lg, db, dp, dp, dp, dp, dp, dp, dp]
     L.kite_ekf_update_batch.argtypes = [vp, lg, lg, dp, dp, dp, dp]
@@ -250,6 +266,16 @@ class Engine:
         self._ck(self.L.kite_colloc_eval(self.ctx, B, B, M, cdp, tau, sxp, sup, _ptr(z), _ptr(p), _ptr(G), _ptr(JX),
                                          _ptr(JU), _ptr(gn)))
         return G, JX, JU, gn
+
+    def colloc_cost(self, z, P, S, qw, tau, sx, cost_params, want_grad=True, out=None):
+        """NMPC performance index + gradient (kite_colloc_cost): z [M*19, B] -> cost [B], grad [M*19, B]."""
+        self._use_torch_stream()
+        M, B = S * P + 1, z.shape[1]
+        self._chk(z, M * 19)
+        qa, qp = _hostarr(qw); sxa, sxp = _hostarr(sx)
+        cost, grad = out if out is not None else (self.empty(B), self.empty(M * 19, B) if want_grad else None)
+        self._ck(self.L.kite_colloc_cost(self.ctx, B, B, P, S, qp, tau, sxp, C.byref(cost_params), _ptr(z), _ptr(cost), _ptr(grad)))
+        return cost, grad
 
     # ---- EKF -----------------------------------------------------------------------------------
     def ekf_predict(self, x, u, dt, P, W, out=None):

@@ -489,6 +489,82 @@ inline void colloc_eval(const Params& P, ModelKind kind, int Pord, int S, double
 }
 
 // ------------------------------------------------------------------------------------
+// NMPC performance index and its gradient (Chebyshev::CollocateCost chebyshev.hpp:280-333 on the Lagrange / Mayer
+// terms of kiteNMPF.cpp:116-143).  Path = circle of given radius / altitude rotated by a quaternion, as both callers
+// build it (nmpf_node.cpp:31-39 tilted by pi/8 about y; kite_control_test.cpp:242-247 untilted).
+//   residual = Sx[6:9] * path(x_s[13] / Sx[13]) - x_s[6:9]                          (kiteNMPF.cpp:120-122)
+//   L(x,u)   = sum Q_c residual_c^2 + W (vref_s - x_s[14])^2 + sum R_m u_s[m]^2      (:123-124)
+//   Mayer(x) = sum Q_c residual_c^2 at node 0 (= final time)                         (:141, chebyshev.hpp:291-295)
+//   cost     = Mayer(X_0) + sum_seg tau * sum_{m=0..P} w_m L(X_{seg*P+m}, U_{seg*P+m})   (chebyshev.hpp:298-330)
+// with Q = 1e2 diag(10,10,100), R = diag(1e-4,1e-1,1e-1,1e-3), W = 1e-3 (kiteNMPF.cpp:32-34) as defaults.
+// ------------------------------------------------------------------------------------
+struct NmpcCost {
+    double Q[3], R[4], W, vref_scaled;          // vref_scaled = Scale_X(14,14) * vel_ref (kiteNMPF.h:34)
+    double radius, altitude, q_rot[4];
+};
+inline NmpcCost nmpc_cost_defaults(const double sx[15], double vel_ref, double radius, double altitude, const double q_rot[4]) {
+    NmpcCost c{{1e2 * 1e1, 1e2 * 1e1, 1e2 * 1e2}, {1e-4, 1e-1, 1e-1, 1e-3}, 1e-3, sx[14] * vel_ref, radius, altitude,
+               {q_rot[0], q_rot[1], q_rot[2], q_rot[3]}};
+    return c;
+}
+template <class T> inline void path_point(const NmpcCost& c, const T& theta, T out[3]) {
+    // Path = [r cos, r sin, alt]; rotated: vec( conj(q) (x) [0,Path] (x) q )          (nmpf_node.cpp:34-39)
+    T q[4] = {T(c.q_rot[0]), T(c.q_rot[1]), T(c.q_rot[2]), T(c.q_rot[3])}, qi[4], Pq[4], t1[4], t2[4];
+    Pq[0] = T(0.0); Pq[1] = T(c.radius) * cos(theta); Pq[2] = T(c.radius) * sin(theta); Pq[3] = T(c.altitude);
+    quat_inverse(q, qi);
+    quat_multiply(qi, Pq, t1);
+    quat_multiply(t1, q, t2);
+    out[0] = t2[1]; out[1] = t2[2]; out[2] = t2[3];
+}
+template <class T> inline T nmpc_path_cost(const NmpcCost& c, const double sx[15], const T xs[15]) {
+    T th = T(1.0 / sx[13]) * xs[13], pp[3], acc = T(0.0);
+    path_point<T>(c, th, pp);
+    for (int i = 0; i < 3; ++i) { T r = T(sx[6 + i]) * pp[i] - xs[6 + i]; acc = acc + T(c.Q[i]) * (r * r); }
+    return acc;
+}
+template <class T> inline T nmpc_lagrange(const NmpcCost& c, const double sx[15], const T xs[15], const T us[4]) {
+    T acc = nmpc_path_cost<T>(c, sx, xs);
+    T dv = T(c.vref_scaled) - xs[14];
+    acc = acc + T(c.W) * (dv * dv);
+    for (int m = 0; m < 4; ++m) acc = acc + T(c.R[m]) * (us[m] * us[m]);
+    return acc;
+}
+// z = [X (M*15) ; U (M*4)]; returns the cost, grad[M*19] (same ordering as z) if non-null.
+inline double colloc_cost(const NmpcCost& c, int Pord, int S, double t0, double tf, const double sx[15], const double* z, double* grad) {
+    const int M = S * Pord + 1;
+    const double tau = (tf - t0) / (2.0 * S);
+    std::vector<double> w = cheb_quad_weights(Pord);
+    const double* X = z; const double* U = z + M * 15;
+    typedef Dual<19> D;
+    if (grad) for (int i = 0; i < M * 19; ++i) grad[i] = 0.0;
+    double cost = 0.0;
+    {   // Mayer term at node 0
+        D xs[15];
+        for (int i = 0; i < 15; ++i) { xs[i] = D(X[i]); xs[i].d[i] = 1.0; }
+        D m = nmpc_path_cost<D>(c, sx, xs);
+        cost += m.v;
+        if (grad) for (int i = 0; i < 15; ++i) grad[i] += m.d[i];
+    }
+    for (int k = 0; k < S; ++k) {
+        double local = 0.0;
+        for (int m = 0; m <= Pord; ++m) {
+            const int n = k * Pord + m;
+            D xs[15], us[4];
+            for (int i = 0; i < 15; ++i) { xs[i] = D(X[n * 15 + i]); xs[i].d[i] = 1.0; }
+            for (int i = 0; i < 4; ++i) { us[i] = D(U[n * 4 + i]); us[i].d[15 + i] = 1.0; }
+            D L = nmpc_lagrange<D>(c, sx, xs, us);
+            local += w[m] * L.v;
+            if (grad) {
+                for (int i = 0; i < 15; ++i) grad[n * 15 + i] += tau * w[m] * L.d[i];
+                for (int i = 0; i < 4; ++i) grad[M * 15 + n * 4 + i] += tau * w[m] * L.d[15 + i];
+            }
+        }
+        cost += tau * local;
+    }
+    return cost;
+}
+
+// ------------------------------------------------------------------------------------
 // EKF (kiteEKF.cpp:6-13, 75-126).  P, W are 13x13 row-major.
 // ------------------------------------------------------------------------------------
 inline void ekf_default_W(double W[169]) {

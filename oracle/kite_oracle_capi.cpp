@@ -115,6 +115,19 @@ void orc_colloc_eval(const double* prm, const double* prm_batch, int kind, int P
     });
 }
 
+// NMPC performance index + gradient: z[n][M*19]; cost[n]; grad[n][M*19] (may be null).  cc = {Q[3],R[4],W,vref_scaled,
+// radius,altitude,q_rot[4]} (15 doubles).
+void orc_colloc_cost(const double* cc, int Pord, int S, double t0, double tf, const double* sx, long n, const double* z,
+                     double* cost, double* grad, int nthreads) {
+    NmpcCost c;
+    std::memcpy(&c, cc, sizeof c);
+    const int M = S * Pord + 1;
+    parallel_for(n, nthreads, [&](long lo, long hi) {
+        for (long i = lo; i < hi; ++i)
+            cost[i] = colloc_cost(c, Pord, S, t0, tf, sx, z + i * (M * 19), grad ? grad + i * (M * 19) : nullptr);
+    });
+}
+
 void orc_ekf_predict(const double* prm, int kind, long n, const double* x, const double* u, double dt, const double* Pc,
                      const double* W, double* xn, double* Pn) {
     const Params& P = as_params(prm);

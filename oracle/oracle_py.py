@@ -147,6 +147,23 @@ class Oracle:
                                  C.c_int(nthreads))
         return G, JX, JU
 
+    @staticmethod
+    def nmpc_cost_params(sx, vel_ref=0.05, radius=2.65, altitude=0.0, q_rot=(1.0, 0.0, 0.0, 0.0), Q=(1e3, 1e3, 1e4),
+                         R=(1e-4, 1e-1, 1e-1, 1e-3), W=1e-3):
+        """15 doubles {Q[3], R[4], W, vref_scaled, radius, altitude, q_rot[4]} (kiteNMPF.cpp:32-34, kiteNMPF.h:34)."""
+        return np.array(list(Q) + list(R) + [W, sx[14] * vel_ref, radius, altitude] + list(q_rot), dtype=np.float64)
+
+    def colloc_cost(self, z, P, S, t0, tf, sx, cc, nthreads=1, want_grad=True):
+        M = S * P + 1
+        z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+        n = z.shape[0]
+        assert z.shape[1] == M * 19 and len(cc) == 15
+        sx = np.ascontiguousarray(sx, dtype=np.float64); cc = np.ascontiguousarray(cc, dtype=np.float64)
+        cost = np.empty(n); grad = np.empty((n, M * 19)) if want_grad else None
+        self.lib.orc_colloc_cost(_p(cc), C.c_int(P), C.c_int(S), C.c_double(t0), C.c_double(tf), _p(sx), C.c_long(n), _p(z),
+                                 _p(cost), _p(grad), C.c_int(nthreads))
+        return cost, grad
+
     def ekf_predict(self, x, u, dt, P, W, kind=KITE):
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)

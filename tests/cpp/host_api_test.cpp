@@ -159,6 +159,15 @@ int main(int argc, char** argv) {
         bool ok = J.size1() == 165 && J.size2() == 209;
         for (int i = 0; ok && i < 165; ++i) for (int j = 0; j < 209; ++j) if (std::fabs(J(i, j) - Jref[(size_t)i * 209 + j]) > 1e-9 * std::fmax(1.0, std::fabs(Jref[(size_t)i * 209 + j]))) { ok = false; std::printf("  J mismatch %d %d\n", i, j); break; }
         CHECK(ok);
+        // performance index of the path-following NMPC (kiteNMPF.cpp:116-143), path of nmpf_node.cpp:31-39
+        std::vector<double> cref = read_vec(gf, "nmpc_cost"), gref = read_vec(gf, "nmpc_grad");
+        DM q_rot{std::cos(M_PI / 8), 0.0, std::sin(M_PI / 8), 0.0};
+        auto cost = spectral.CollocateCost(kite, spectral.DefaultCost(DM::diag(DM(sx)), 0.05, 2.65, 0.0, q_rot), DM::diag(DM(sx)), 0.0, 1.0);
+        DM grad;
+        const double cv = cost->eval(DM(z), grad);
+        CHECK(std::fabs(cv - cref[0]) <= 1e-9 * std::fabs(cref[0]));
+        CHECK(close_vec(grad, gref, 1e-9));
+        CHECK(std::fabs((*cost)(DM(z)) - cv) == 0.0);
     }
 
     // ---- identification variant (kite.cpp:365-616): dynamics(x,u,p) ------------------------------------------

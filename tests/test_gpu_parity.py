@@ -265,6 +265,24 @@ def test_colloc_vs_oracle_batch_with_param_perturbation(eng, oracle, golden, yam
     assert_close(aos(JU, M, 15, 4), rJU, RTOL, what="JU batch")
 
 
+def test_nmpc_cost_vs_oracle_batch(eng, okb, oracle, golden):
+    """8f row 1: collocated NMPC cost + gradient (chebyshev.hpp:280-333, kiteNMPF.cpp:116-143), tilted and flat path."""
+    from openkite_b200.collocation import quad_weights
+    c = golden["colloc_nmpc_P5_S2_scaled"]
+    B = 300
+    rng = np.random.default_rng(9)
+    z = np.array(c["z"])[None, :] * (1 + 0.05 * rng.standard_normal((B, 209)))
+    for q, alt in (((np.cos(np.pi / 8), 0.0, np.sin(np.pi / 8), 0.0), 0.0), ((1.0, 0.0, 0.0, 0.0), 1.5)):
+        cc = oracle.nmpc_cost_params(c["sx"], q_rot=q, altitude=alt)
+        rcost, rgrad = oracle.colloc_cost(z, 5, 2, 0.0, 1.0, c["sx"], cc, nthreads=4)
+        cp = okb.NmpcCost.defaults(c["sx"], q_rot=q, altitude=alt)
+        cost, grad = eng.colloc_cost(soa(z), 5, 2, quad_weights(5), 0.25, c["sx"], cp)
+        assert_close(cost.cpu().numpy(), rcost, RTOL, what="nmpc cost")
+        assert_close(aos(grad), rgrad, RTOL, what="nmpc cost gradient")
+    cost1, none = eng.colloc_cost(soa(z[:1]), 5, 2, quad_weights(5), 0.25, c["sx"], cp, want_grad=False)   # B = 1, no gradient
+    assert none is None and abs(cost1.item() - rcost[0]) <= RTOL * abs(rcost[0])
+
+
 def test_ekf_predict_vs_oracle_batch(eng, oracle):
     B, dt = 515, 0.0084
     x = oracle.synth_x0(0, B); u = oracle.synth_controls(0, B, 1)[:, 0, :]

@@ -56,6 +56,9 @@ def test_host_api_on_gpu(host_bin, yaml_path, golden, oracle, tmp_path):
         J[k * 15:(k + 1) * 15, k * 15:(k + 1) * 15] -= tau * JX[k]
         J[k * 15:(k + 1) * 15, 165 + k * 4:165 + (k + 1) * 4] = -tau * JU[k]
     put("colloc_sx", cc["sx"]); put("colloc_su", cc["su"]); put("colloc_z", cc["z"]); put("colloc_G", cc["G"]); put("colloc_J", J)
+    ncc = oracle.nmpc_cost_params(cc["sx"], q_rot=(np.cos(np.pi / 8), 0.0, np.sin(np.pi / 8), 0.0))
+    ncost, ngrad = oracle.colloc_cost(np.array(cc["z"]), 5, 2, 0.0, 1.0, cc["sx"], ncc)
+    put("nmpc_cost", ncost); put("nmpc_grad", ngrad[0])
     idc = golden["rhs_id"]["nominal"]
     put("id_p", idc["p"]); put("id_f", idc["f"])
     gpath = tmp_path / "host_golden.txt"

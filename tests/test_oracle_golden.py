@@ -184,3 +184,47 @@ def test_python_collocation_operators_match_oracle(oracle):
         assert_close(quad_weights(P), np.ravel(oracle.cheb_weights(P)), 1e-13, what="weights")
         assert_close(comp_diff_matrix(P, S), oracle.cheb_compdiff(P, S), 1e-13, what="compD")
     assert abs(diff_matrix(5)[0, 0] - 8.5) < 1e-13 and abs(quad_weights(5).sum() - 2.0) < 1e-14
+
+
+def _nmpc_case(golden):
+    c = golden["colloc_nmpc_P5_S2_scaled"]
+    q = (np.cos(np.pi / 8), 0.0, np.sin(np.pi / 8), 0.0)          # nmpf_node.cpp:35
+    return np.array(c["z"]), np.array(c["sx"]), q
+
+
+def nmpc_cost_closed_form(z, sx, q, P=5, S=2, tf=1.0, vel_ref=0.05, radius=2.65, alt=0.0):
+    """Independent numpy restatement of the NMPC performance index (rotation-matrix form of the tilted circle)."""
+    from openkite_b200.collocation import quad_weights
+    M = S * P + 1
+    X, U = z[:M * 15].reshape(M, 15), z[M * 15:].reshape(M, 4)
+    s0, v = q[0], np.array(q[1:])
+    Rm = (s0 * s0 - v @ v) * np.eye(3) + 2 * np.outer(v, v) + 2 * s0 * np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    Q = np.array([1e3, 1e3, 1e4]); R = np.array([1e-4, 1e-1, 1e-1, 1e-3]); W = 1e-3
+    def pathcost(x):
+        th = x[13] / sx[13]
+        pp = Rm.T @ np.array([radius * np.cos(th), radius * np.sin(th), alt])
+        r = sx[6:9] * pp - x[6:9]
+        return float(Q @ (r * r))
+    w, tau = quad_weights(P), tf / (2 * S)
+    cost = pathcost(X[0])
+    for k in range(S):
+        for m in range(P + 1):
+            n = k * P + m
+            cost += tau * w[m] * (pathcost(X[n]) + W * (sx[14] * vel_ref - X[n, 14]) ** 2 + float(R @ (U[n] ** 2)))
+    return cost
+
+
+def test_nmpc_cost_and_gradient(oracle, golden):
+    """chebyshev.hpp:280-333 + kiteNMPF.cpp:116-143: oracle cost vs an independent closed form, gradient vs central differences."""
+    z, sx, q = _nmpc_case(golden)
+    cc = oracle.nmpc_cost_params(sx, q_rot=q)
+    cost, g = oracle.colloc_cost(z, 5, 2, 0.0, 1.0, sx, cc)
+    assert abs(cost[0] - nmpc_cost_closed_form(z, sx, q)) <= 1e-12 * abs(cost[0])
+    rng = np.random.default_rng(5)
+    for i in rng.choice(209, 40, replace=False):
+        e = np.zeros(209); e[i] = 1e-6
+        fd = (nmpc_cost_closed_form(z + e, sx, q) - nmpc_cost_closed_form(z - e, sx, q)) / 2e-6
+        assert abs(fd - g[0, i]) <= 1e-6 * max(1.0, abs(g[0, i])), i
+    # structure: only r (6..8), theta (13), theta_dot (14) and the controls carry gradient
+    gx = g[0, :165].reshape(11, 15)
+    assert np.all(gx[:, [0, 1, 2, 3, 4, 5, 9, 10, 11, 12]] == 0.0)
