@@ -524,7 +524,7 @@ __device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, cons
 template <bool ARM, bool RIGID>
 __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const __grid_constant__ EkfArgs a) {
     using C = EfCfg<ARM>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* const Jt = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::PER_WARP;
     double* const Qt = Jt + 8 * C::PS;
