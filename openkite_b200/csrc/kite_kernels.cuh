@@ -152,34 +152,49 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
     AeroCoef A = a.K.A;
     if constexpr (PERCOEF) load_coef(a.K, a.p, a.ld, i, A);
 
-    // first control
-    if constexpr (UMODE == 0 || UMODE == 1) {
+    // Controls of step k.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 2 are pulled into
+    // L2 by a register-free prefetch while step k computes, and the (then short-latency) load itself happens at the top
+    // of the step -- holding the next step's controls in registers across the step cost 6 registers the RHS needs
+    // (KITE_ROLLOUT_REGPREFETCH=1 restores that variant; measured slower, profiles/r1u).
+#ifndef KITE_ROLLOUT_REGPREFETCH
+#define KITE_ROLLOUT_REGPREFETCH 0
+#endif
+    auto load_u = [&](long k, double (&uu)[3]) {
+        if constexpr (UMODE == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) un[c] = __ldg(a.u + (long)c * a.ld + i);
-    } else if constexpr (UMODE == 2) {
+            for (int c = 0; c < 3; ++c) uu[c] = __ldg(a.u + (long)c * a.ld + i);
+        } else if constexpr (UMODE == 1) {
+            const double* up = a.u + k * 3 * a.ld + i;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) un[c] = __ldg(a.u + c);
-    } else {
-        synth_control((uint64_t)(a.index0 + i), 0, un);
-    }
+            for (int c = 0; c < 3; ++c) uu[c] = __ldg(up + (long)c * a.ld);
+        } else if constexpr (UMODE == 2) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) uu[c] = __ldg(a.u + k * 3 + c);
+        } else {
+            synth_control((uint64_t)(a.index0 + i), (uint64_t)k, uu);
+        }
+    };
+    if (a.N > 0) load_u(0, un);
     double cost = 0.0;
     const double Qc[13] = {1e3, 1e2, 1e2, 1e2, 1e2, 1e2, 1e1, 1e1, 1e2, 1e2, 1e2, 1e2, 1e2};  // kite_identification_test.cpp:193
     long next_save = a.save_every;
     long saved = 0;
     for (long k = 0; k < a.N; ++k) {
+        if constexpr (UMODE == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) u[c] = un[c];
-        // software prefetch of the next step's controls: the load is in flight during the 4 RHS evaluations
-        if (k + 1 < a.N) {
+            for (int c = 0; c < 3; ++c) u[c] = un[c];
+        } else if constexpr (KITE_ROLLOUT_REGPREFETCH) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = un[c];
+            if (k + 1 < a.N) load_u(k + 1, un);      // in flight during the 4 RHS evaluations
+        } else {
+            load_u(k, u);
             if constexpr (UMODE == 1) {
-                const double* up = a.u + (long)(k + 1) * 3 * a.ld + i;
+                if ((threadIdx.x & 15) == 0 && k + 2 < a.N) {          // one prefetch per 128-byte line
+                    const double* up = a.u + (k + 2) * 3 * a.ld + i;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) un[c] = __ldg(up + (long)c * a.ld);
-            } else if constexpr (UMODE == 2) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) un[c] = __ldg(a.u + (k + 1) * 3 + c);
-            } else if constexpr (UMODE == 3) {
-                synth_control((uint64_t)(a.index0 + i), (uint64_t)(k + 1), un);
+                    for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(up + (long)c * a.ld));
+                }
             }
         }
         if constexpr (SMEM) rk4_step_xsmem<RIGID>(a.K, A, sx, ROLLOUT_BLOCK, x, u, a.h);
@@ -356,6 +371,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
 
     for (long g = gw; g < ngroups; g += nwarps) {
         // ---------------- phase A: lane = unit --------------------------------------------------------------
+#ifndef KITE_SF_SKIP_A      // (developer timing switch: skip one phase to profile the other alone; results are garbage)
         {
             const long unit = g * 32 + lane;
             // the step base state and the tableau accumulator are parked in shared memory ([13][32] columns): the
@@ -384,8 +400,10 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
             }
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores above -> async-proxy (bulk copy) reads below
+#endif
         __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
         prefetch_inputs(g + nwarps);                    // next group's x, u land in shared memory behind phase B
+#ifndef KITE_SF_SKIP_B
 
         // ---------------- phase B: 8 lanes = unit, 4 units per pass -------------------------------------------
 #pragma unroll 1
@@ -462,6 +480,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
                 }
             }
         }
+#endif
         __syncwarp();                                   // every lane is done reading the ring before the next group
     }
     __pipeline_wait_prior(0);

@@ -88,6 +88,23 @@ __device__ __forceinline__ void dM_dq_apply(double s, const double (&a)[3], cons
     }
 }
 
+// Attitude matrix M(q) = (s^2 - a.a) I + 2 a a^T + 2 s [a]x and the squared norm nq = |q|^2 in 21 FP64 operations:
+// doubled vector part t = 2a, off-diagonals as one FMA each, M11 and M22 from M00 by two-term corrections.
+__device__ __forceinline__ void attitude_matrix(double s, const double (&a)[3], double (&M)[3][3], double& nq) {
+    const double t0 = a[0] + a[0], t1 = a[1] + a[1], t2 = a[2] + a[2];
+    const double st0 = s * t0, st1 = s * t1, st2 = s * t2;
+    M[0][1] = fma(t0, a[1], -st2); M[1][0] = fma(t0, a[1], st2);
+    M[0][2] = fma(t0, a[2], st1);  M[2][0] = fma(t0, a[2], -st1);
+    M[1][2] = fma(t1, a[2], -st0); M[2][1] = fma(t1, a[2], st0);
+    const double p = fma(s, s, a[0] * a[0]);
+    const double r = fma(a[1], a[1], a[2] * a[2]);
+    M[0][0] = p - r;
+    nq = p + r;
+    const double q0 = fma(-t0, a[0], M[0][0]);
+    M[1][1] = fma(t1, a[1], q0);
+    M[2][2] = fma(t2, a[2], q0);
+}
+
 struct NoSink {
     __device__ __forceinline__ void jx(int, int, double) const {}
     __device__ __forceinline__ void ju(int, int, double) const {}
@@ -143,16 +160,8 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     const double Fz = fma(ca, Zde, Z1);
 
     // ---- attitude matrix M(q):  q (x) [0,y] (x) conj(q) = M y,   conj(q) (x) [0,y] (x) q = M^T y ----
-    const double s2 = s * s, a00 = a[0] * a[0], a11 = a[1] * a[1], a22 = a[2] * a[2];
-    const double a01 = a[0] * a[1], a02 = a[0] * a[2], a12 = a[1] * a[2];
-    const double sa0 = s * a[0], sa1 = s * a[1], sa2 = s * a[2];
-    double M[3][3];
-    M[0][0] = (s2 + a00) - (a11 + a22);
-    M[1][1] = (s2 + a11) - (a00 + a22);
-    M[2][2] = (s2 + a22) - (a00 + a11);
-    M[0][1] = 2.0 * (a01 - sa2); M[1][0] = 2.0 * (a01 + sa2);
-    M[0][2] = 2.0 * (a02 + sa1); M[2][0] = 2.0 * (a02 - sa1);
-    M[1][2] = 2.0 * (a12 - sa0); M[2][1] = 2.0 * (a12 + sa0);
+    double M[3][3], nq;
+    attitude_matrix(s, a, M, nq);
 
     double vi[3];   // inertial velocity = r_dot
 #pragma unroll
@@ -171,12 +180,13 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     double m[3];    // M^T n
 #pragma unroll
     for (int i = 0; i < 3; ++i) m[i] = fma(M[0][i], n[0], fma(M[1][i], n[1], M[2][i] * n[2]));
-    const double Rb[3] = {-tau * m[0], -tau * m[1], -tau * m[2]};
+    const double Rb[3] = {-tau * m[0], -tau * m[1], -tau * m[2]};     // only consumed by the tether-arm moment and the Jacobian
 
     // ---- v_dot = (Faero + T e1 + R_b)/m + g M^T e3 - w x v ---------------------------------
-    f[0] = fma(Fx + u[0] + Rb[0], K.inv_mass, fma(K.g, M[2][0], -(w[1] * v[2] - w[2] * v[1])));
-    f[1] = fma(Fy + Rb[1], K.inv_mass, fma(K.g, M[2][1], -(w[2] * v[0] - w[0] * v[2])));
-    f[2] = fma(Fz + Rb[2], K.inv_mass, fma(K.g, M[2][2], -(w[0] * v[1] - w[1] * v[0])));
+    const double tm = -tau * K.inv_mass;                              // R_b / mass = tm * m
+    f[0] = fma(tm, m[0], fma(Fx + u[0], K.inv_mass, fma(K.g, M[2][0], fma(w[2], v[1], -w[1] * v[2]))));
+    f[1] = fma(tm, m[1], fma(Fy, K.inv_mass, fma(K.g, M[2][1], fma(w[0], v[2], -w[2] * v[0]))));
+    f[2] = fma(tm, m[2], fma(Fz, K.inv_mass, fma(K.g, M[2][2], fma(w[1], v[0], -w[0] * v[1]))));
 
     // ---- moments ---------------------------------------------------------------------------
     const double qSb = qS * K.b, qSc = qS * K.c;
@@ -207,11 +217,12 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
 
     // ---- kinematics --------------------------------------------------------------------------
     f[6] = vi[0]; f[7] = vi[1]; f[8] = vi[2];
-    const double mu = 0.5 * K.lambda * (((s2 + a00) + (a11 + a22)) - 1.0);
-    f[9] = fma(mu, s, -0.5 * fma(a[0], w[0], fma(a[1], w[1], a[2] * w[2])));
-    f[10] = fma(mu, a[0], 0.5 * (fma(s, w[0], a[1] * w[2] - a[2] * w[1])));
-    f[11] = fma(mu, a[1], 0.5 * (fma(s, w[1], a[2] * w[0] - a[0] * w[2])));
-    f[12] = fma(mu, a[2], 0.5 * (fma(s, w[2], a[0] * w[1] - a[1] * w[0])));
+    const double mu = (0.5 * K.lambda) * (nq - 1.0);
+    const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};         // q_dot = q (x) [0, w/2] + mu q
+    f[9] = fma(mu, s, -fma(a[0], hw[0], fma(a[1], hw[1], a[2] * hw[2])));
+    f[10] = fma(mu, a[0], fma(s, hw[0], fma(a[1], hw[2], -a[2] * hw[1])));
+    f[11] = fma(mu, a[1], fma(s, hw[1], fma(a[2], hw[0], -a[0] * hw[2])));
+    f[12] = fma(mu, a[2], fma(s, hw[2], fma(a[0], hw[1], -a[1] * hw[0])));
 
     if constexpr (JAC) {
         // =========================== gradients w.r.t. v of the aero scalars =======================
@@ -426,25 +437,18 @@ __device__ __forceinline__ void rigid_eval(const KiteConsts& K, const double (&x
     const double w[3] = {x[3], x[4], x[5]};
     const double s = x[9];
     const double a[3] = {x[10], x[11], x[12]};
-    const double s2 = s * s, a00 = a[0] * a[0], a11 = a[1] * a[1], a22 = a[2] * a[2];
-    const double a01 = a[0] * a[1], a02 = a[0] * a[2], a12 = a[1] * a[2];
-    const double sa0 = s * a[0], sa1 = s * a[1], sa2 = s * a[2];
-    double M[3][3];
-    M[0][0] = (s2 + a00) - (a11 + a22);
-    M[1][1] = (s2 + a11) - (a00 + a22);
-    M[2][2] = (s2 + a22) - (a00 + a11);
-    M[0][1] = 2.0 * (a01 - sa2); M[1][0] = 2.0 * (a01 + sa2);
-    M[0][2] = 2.0 * (a02 + sa1); M[2][0] = 2.0 * (a02 - sa1);
-    M[1][2] = 2.0 * (a12 - sa0); M[2][1] = 2.0 * (a12 + sa0);
+    double M[3][3], nq;
+    attitude_matrix(s, a, M, nq);
 #pragma unroll
     for (int i = 0; i < 6; ++i) f[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) f[6 + i] = fma(M[i][0], v[0], fma(M[i][1], v[1], M[i][2] * v[2]));
-    const double mu = 0.5 * K.lambda * (((s2 + a00) + (a11 + a22)) - 1.0);
-    f[9] = fma(mu, s, -0.5 * fma(a[0], w[0], fma(a[1], w[1], a[2] * w[2])));
-    f[10] = fma(mu, a[0], 0.5 * (fma(s, w[0], a[1] * w[2] - a[2] * w[1])));
-    f[11] = fma(mu, a[1], 0.5 * (fma(s, w[1], a[2] * w[0] - a[0] * w[2])));
-    f[12] = fma(mu, a[2], 0.5 * (fma(s, w[2], a[0] * w[1] - a[1] * w[0])));
+    const double mu = (0.5 * K.lambda) * (nq - 1.0);
+    const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};         // q_dot = q (x) [0, w/2] + mu q
+    f[9] = fma(mu, s, -fma(a[0], hw[0], fma(a[1], hw[1], a[2] * hw[2])));
+    f[10] = fma(mu, a[0], fma(s, hw[0], fma(a[1], hw[2], -a[2] * hw[1])));
+    f[11] = fma(mu, a[1], fma(s, hw[1], fma(a[2], hw[0], -a[0] * hw[2])));
+    f[12] = fma(mu, a[2], fma(s, hw[2], fma(a[0], hw[1], -a[1] * hw[0])));
     if constexpr (JAC) {
         double dvi_q[3][4];
         dM_dq_apply<+1>(s, a, v, dvi_q);

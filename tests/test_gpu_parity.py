@@ -232,6 +232,36 @@ def test_sens_rollout_vs_oracle(eng, oracle):
     assert_close(Gam.cpu().numpy().transpose(2, 0, 1).reshape(B, N, 13, 3), rGam, RTOL, what="Gamma")
 
 
+def test_padded_leading_dimension(eng, okb, oracle):
+    """ld > B: units live in the first B columns of wider SoA buffers (sub-batches of a larger allocation)."""
+    import ctypes as C
+    B, ld, h = 77, 128, 0.01
+    x = oracle.synth_x0(3, B); u = oracle.synth_controls(3, B, 1)[:, 0, :]
+    xd = torch.zeros(13, ld, dtype=torch.float64, device="cuda"); xd[:, :B] = soa(x)
+    ud = torch.zeros(3, ld, dtype=torch.float64, device="cuda"); ud[:, :B] = soa(u)
+    xn = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda")
+    Phi = torch.full((169, ld), -7.0, dtype=torch.float64, device="cuda"); Gam = torch.full((39, ld), -7.0, dtype=torch.float64, device="cuda")
+    w = eng.workspace(eng.L.kite_rk4_sens_work_bytes(B))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    eng._use_torch_stream()
+    eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, B, ld, h, p(xd), p(ud), p(xn), p(Phi), p(Gam), p(w)))
+    rxn, rPhi, rGam = oracle.rk4_sens(x, u, h)
+    assert_close(aos(xn[:, :B]), rxn, RTOL, what="xn ld>B"); assert_close(aos(Phi[:, :B], 13, 13), rPhi, RTOL, what="Phi ld>B")
+    assert_close(aos(Gam[:, :B], 13, 3), rGam, RTOL, what="Gamma ld>B")
+    assert float((xn[:, B:] + 7.0).abs().max()) == 0.0 and float((Phi[:, B:] + 7.0).abs().max()) == 0.0   # padding untouched
+    W, _ = oracle.ekf_defaults()
+    Pd = torch.zeros(169, ld, dtype=torch.float64, device="cuda"); Pd[:, :B] = torch.from_numpy((10 * W).reshape(169, 1)).cuda()
+    Pn = torch.full((169, ld), -7.0, dtype=torch.float64, device="cuda")
+    Wh = np.ascontiguousarray(W)
+    eng._ck(eng.L.kite_ekf_predict_batch(eng.ctx, B, ld, 0.0084, p(xd), p(ud), p(Pd), Wh.ctypes.data_as(C.c_void_p), p(xn), p(Pn), None))
+    rxe, rPe = oracle.ekf_predict(x, u, 0.0084, np.tile(10 * W, (B, 1, 1)), W)
+    assert_close(aos(Pn[:, :B], 13, 13), rPe, RTOL, what="EKF Pn ld>B"); assert_close(aos(xn[:, :B]), rxe, RTOL, what="EKF xn ld>B")
+    assert float((Pn[:, B:] + 7.0).abs().max()) == 0.0
+    xf = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda")
+    eng._ck(eng.L.kite_rk4_rollout(eng.ctx, B, ld, 25, 1e-3, p(xd), p(ud), okb.U_CONST, None, p(xf), None, 0, None, None, None, 0))
+    assert_close(aos(xf[:, :B]), oracle.rollout(x, u, 25, 1e-3), RTOL, what="rollout ld>B")
+
+
 def test_sens_linearity_property(eng, oracle):
     """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
     B, h = 2048, 0.02
