@@ -50,17 +50,23 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index = index; self.proc = None; self.lines = []
+        self.index = index; self.proc = None; self.lines = []; self.lo = 0; self.hi = None
+
+    def mark_begin(self):      # samples before this point (warm-up) are ignored
+        self.lo = len(self.lines)
+
+    def mark_end(self):
+        self.hi = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
@@ -79,7 +85,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.lo:self.hi]:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -169,10 +175,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()       # started before the warm-up: nvidia-smi needs ~0.3 s to come up
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark_begin()
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ek = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -185,6 +192,7 @@ def main():
             dist.all_gather_into_tensor(gathered, xf.view(-1))
     e1.record()
     barrier()
+    sampler.mark_end()
     launches = eng.launch_count - l0
     ms_total = e0.elapsed_time(e1)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ek)     # the rollout kernel alone, on its launch stream
