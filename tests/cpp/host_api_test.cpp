@@ -11,6 +11,8 @@
 #include "openkite/chebyshev.hpp"
 #include "openkite/integrator.hpp"
 #include "openkite/kiteEKF.hpp"
+#include "openkite/simulator.hpp"
+#include <sstream>
 
 using namespace openkite;
 
@@ -137,6 +139,25 @@ int main(int argc, char** argv) {
         KiteEKF est3(odd, kite.getNumericJacobian());
         est3.setEstimation(x_est); est3.propagate(dt);
         CHECK(close_vec(est3.getEstimation(), x_est.nonzeros(), 0.0));
+    }
+
+    // ---- Simulator stepping loop and record formats (simulator.cpp:43-74, simple_logger.cpp:63-85) ----------
+    {
+        Function ode = kite.getNumericDynamics();
+        ODESolver stepper(ode, {{"tf", 0.001}, {"method", (double)RK4}});
+        Simulator sim(stepper);
+        CHECK(!sim.is_initialized());
+        sim.initialize(init_state);
+        sim.setControls(0.1, 0.0, 0.0);
+        for (int k = 0; k < 1000; ++k) sim.simulate();
+        CHECK(close_vec(sim.getState(), read_vec(gf, "config1_after_1000b"), 1e-9));
+        CHECK(sim.getPose().numel() == 7 && sim.getPose()[3] == sim.getState()[9]);
+        std::ostringstream os;
+        sim.write_state(os, 12.5); sim.write_pose(os, 12.5);
+        std::istringstream is(os.str());
+        std::string l1, l2; std::getline(is, l1); std::getline(is, l2);
+        int n1 = 0, n2 = 0; { std::istringstream a(l1), b(l2); double v; while (a >> v) ++n1; while (b >> v) ++n2; }
+        CHECK(n1 == 14 && n2 == 8 && l1.rfind("12.50000000 ", 0) == 0);
     }
 
     // ---- rigid body (kite_control_test.cpp:12-44) --------------------------------------------------------

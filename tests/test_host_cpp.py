@@ -44,6 +44,7 @@ def test_host_api_on_gpu(host_bin, yaml_path, golden, oracle, tmp_path):
     z = np.array([1.4522, -3.1274, -1.7034, -0.5455, -0.2382, -0.2922, -0.7485])
     xu, Pu = oracle.ekf_update(z, V, np.array(e["xn"]), np.array(e["Pn"])[None])
     put("ekf_est", xu[0])
+    put("config1_after_1000b", r["1000"])
     rb = golden["rigid_body"]
     put("rb_f", rb["f"]); put("rb_xn", rb["xn"])
     cc = golden["colloc_nmpc_P5_S2_scaled"]
