@@ -135,14 +135,11 @@ constexpr int ROLLOUT_BLOCK = KITE_ROLLOUT_BLOCK;
 #define KITE_ROLLOUT_ATTR __launch_bounds__(ROLLOUT_BLOCK, 3)
 #endif
 
-template <int UMODE, bool RIGID, bool PERCOEF, bool SMEM>
+template <int UMODE, bool RIGID, bool PERCOEF>
 __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
-    // SMEM: the step base state is parked in shared memory during the four stages (rk4_step_xsmem), [13][block] columns
-    __shared__ double sh[SMEM ? 13 * ROLLOUT_BLOCK : 1];
-    double* const sx = sh + threadIdx.x;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.B) return;
-    double x[13], u[3], un[3];
+    double x[13], u[3];
     if constexpr (UMODE == 3) {
         synth_x0((uint64_t)(a.index0 + i), x);
     } else {
@@ -154,11 +151,8 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
 
     // Controls of step k.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 2 are pulled into
     // L2 by a register-free prefetch while step k computes, and the (then short-latency) load itself happens at the top
-    // of the step -- holding the next step's controls in registers across the step cost 6 registers the RHS needs
-    // (KITE_ROLLOUT_REGPREFETCH=1 restores that variant; measured slower, profiles/r1u).
-#ifndef KITE_ROLLOUT_REGPREFETCH
-#define KITE_ROLLOUT_REGPREFETCH 0
-#endif
+    // of the step -- holding the next step's controls in registers across the step costs 6 registers the RHS needs
+    // (measured: 61.5 % instead of 65.0 % of FP64 peak, profiles/r1u).
     auto load_u = [&](long k, double (&uu)[3]) {
         if constexpr (UMODE == 0) {
 #pragma unroll
@@ -174,20 +168,13 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
             synth_control((uint64_t)(a.index0 + i), (uint64_t)k, uu);
         }
     };
-    if (a.N > 0) load_u(0, un);
+    if constexpr (UMODE == 0) load_u(0, u);         // one control per trajectory, held for all steps
     double cost = 0.0;
     const double Qc[13] = {1e3, 1e2, 1e2, 1e2, 1e2, 1e2, 1e1, 1e1, 1e2, 1e2, 1e2, 1e2, 1e2};  // kite_identification_test.cpp:193
     long next_save = a.save_every;
     long saved = 0;
     for (long k = 0; k < a.N; ++k) {
-        if constexpr (UMODE == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) u[c] = un[c];
-        } else if constexpr (KITE_ROLLOUT_REGPREFETCH) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) u[c] = un[c];
-            if (k + 1 < a.N) load_u(k + 1, un);      // in flight during the 4 RHS evaluations
-        } else {
+        if constexpr (UMODE != 0) {
             load_u(k, u);
             if constexpr (UMODE == 1) {
                 if ((threadIdx.x & 15) == 0 && k + 2 < a.N) {          // one prefetch per 128-byte line
@@ -197,8 +184,7 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
                 }
             }
         }
-        if constexpr (SMEM) rk4_step_xsmem<RIGID>(a.K, A, sx, ROLLOUT_BLOCK, x, u, a.h);
-        else rk4_step<RIGID>(a.K, A, x, u, a.h);
+        rk4_step<RIGID>(a.K, A, x, u, a.h);
         if (a.y) {                                  // uniform branch: identification cost fused into the rollout
             double e = 0.0;
 #pragma unroll

@@ -508,30 +508,6 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A,
     for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }
 
-// Variant with only the step base state x parked in shared memory (column of this thread, stride = blockDim): the
-// stage input, the RHS temporaries and the tableau accumulator stay in registers.  Frees 26 registers against rk4_step
-// at the price of 52 LDS + 13 STS per step (~4% of the FP64 instruction count).  On return xt holds the new state.
-template <bool RIGID>
-__device__ __forceinline__ void rk4_step_xsmem(const KiteConsts& K, const AeroCoef& A, double* __restrict__ sx, int stride,
-                                               double (&xt)[13], const double (&u)[3], double h) {
-    NoSink ns;
-    double k[13], acc[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { sx[i * stride] = xt[i]; acc[i] = 0.0; }
-    const double hh = 0.5 * h;
-#pragma unroll 1
-    for (int st = 0; st < 4; ++st) {
-        model_eval<RIGID, false>(K, A, xt, u, k, ns);
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-        const double an = (st == 2) ? h : hh;
-#pragma unroll
-        for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], sx[i * stride]); }
-    }
-    const double h6 = h / 6.0;
-#pragma unroll
-    for (int i = 0; i < 13; ++i) xt[i] = fma(h6, acc[i], sx[i * stride]);
-}
-
 // ---- counter-based synthetic inputs (workload definition; identical to oracle::counter_uniform) ----
 __host__ __device__ inline uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ULL;
