@@ -99,6 +99,26 @@ def test_config3_full_size_sensitivities(eng, oracle):
     assert float((P0 - eye).abs().max()) < 1e-8 and float(G0.abs().max()) < 1e-8
 
 
+def test_sensitivity_kernel_is_schedule_independent(eng):
+    """The fused sensitivity kernel hands stage Jacobians from phase A to phase B through a per-warp L2 scratch and TMA
+    bulk copies (generic -> async proxy).  A stale or torn tile would show up as a schedule-dependent result: the same
+    1,048,576 units computed (a) twice in one launch each and (b) as 61 launches of odd sizes (different warp -> unit
+    mapping, different scratch reuse pattern) must agree bit for bit."""
+    B = 1 << 20
+    x0, u = eng.synth_inputs(B, 1)
+    u0 = u[0].contiguous()
+    a = eng.sens_step(x0, u0, 0.02)
+    b = eng.sens_step(x0, u0, 0.02)
+    for ta, tb in zip(a, b):
+        assert torch.equal(ta, tb)
+    chunk = 17203                                            # odd, not a multiple of 32
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        c = eng.sens_step(x0[:, lo:hi].contiguous(), u0[:, lo:hi].contiguous(), 0.02)
+        for ta, tc in zip(a, c):
+            assert torch.equal(ta[:, lo:hi], tc), (lo, hi)
+
+
 def test_config4_full_size_collocation(eng, okb, oracle, golden):
     """config 4: 65,536 NMPC scenarios (P = 5, S = 2, nmpf_node scaling): G, dG blocks, cost and gradient."""
     from openkite_b200.collocation import comp_diff_matrix, quad_weights
