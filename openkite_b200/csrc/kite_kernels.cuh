@@ -9,7 +9,6 @@
 // =====================================================================================
 #pragma once
 #include <cuda_pipeline.h>
-#include <cuda/annotated_ptr>
 
 #include "kite_model.cuh"
 
@@ -258,25 +257,28 @@ struct SensArgs {
 constexpr int SF_WARPS = KITE_SF_WARPS;        // warps per CTA (one CTA per SM): scratch footprint = SMs x warps x 114 KB
 constexpr int SF_RING = 4;                     // stage tiles in flight per warp
 template <bool ARM> struct SfCfg {
+    static constexpr int WARPS = ARM ? (SF_WARPS < 5 ? SF_WARPS : 5) : SF_WARPS;   // shared memory: 36 / 42 KB per warp
     static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;      // slots a stage Jacobian occupies
     static constexpr int TILE = NS * 4;                               // doubles per tile: [slot][4 units], contiguous in scratch
     static constexpr int TILE_S = TILE + 4;                           // shared-memory tile: + one zero row (gather target)
     static constexpr unsigned TILE_BYTES = TILE * 8;                  // one bulk copy (multiple of 16)
     static constexpr long SCRATCH_PER_WARP = 4L * 8 * TILE;           // doubles: [stage][pass][slot][4]
-    // dynamic shared memory: ring tiles | phase-A columns x[13][32], acc[13][32], u[3][32] per warp | mbarriers
-    static constexpr size_t SMEM_RING = sizeof(double) * SF_WARPS * SF_RING * TILE_S;
-    static constexpr size_t SMEM_XA = sizeof(double) * SF_WARPS * 29 * 32;
-    static constexpr size_t SMEM = SMEM_RING + SMEM_XA + sizeof(unsigned long long) * SF_WARPS * SF_RING;
+    // phase-A staging tile of one stage, [pass][slot][4 units] with the pass stride == 4 (mod 16) doubles so that the
+    // 8 four-lane groups of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
+    static constexpr int PS = TILE + (TILE % 16 == 12 ? 8 : (TILE % 16 == 0 ? 4 : (20 - TILE % 16) % 16));
+    // per-warp shared memory: staging (phase A) and the tile ring (phase B) share one region; + x[13], acc[13], u[3] columns
+    static constexpr int UNION = (8 * PS > SF_RING * TILE_S) ? 8 * PS : SF_RING * TILE_S;
+    static constexpr size_t SMEM_RING = sizeof(double) * WARPS * UNION;
+    static constexpr size_t SMEM_XA = sizeof(double) * WARPS * 29 * 32;
+    static constexpr size_t SMEM = SMEM_RING + SMEM_XA + sizeof(unsigned long long) * WARPS * SF_RING;
 };
+static_assert(SfCfg<false>::PS % 16 == 4 && SfCfg<true>::PS % 16 == 4 && SfCfg<false>::PS % 2 == 0, "staging pass stride");
 constexpr long SF_SCRATCH_PER_WARP_MAX = 4L * 8 * JAC_SLOTS * 4;
 
-// L2 residency hints: the scratch is tagged evict_last (persisting) when written and when read back, everything that
-// streams through once (inputs, xn, Phi, Gamma) is evict_first, so the streaming output does not push the scratch out.
-typedef cuda::annotated_ptr<double, cuda::access_property::persisting> PersistPtr;
-struct WarpSink {       // compact slots of this lane's unit: [pass = lane / 4][slot][lane % 4]
-    PersistPtr base;    // &Jw[stage][lane / 4][0][lane % 4]: a warp store fills 8 whole 32-byte sectors
-    __device__ __forceinline__ void jx(int i, int j, double v) { base[jx_slot(i, j) * 4] = v; }
-    __device__ __forceinline__ void ju(int i, int j, double v) { base[ju_slot(i, j) * 4] = v; }
+struct StageSink {      // phase-A staging tile of the warp: compact slots of this lane's unit at [lane / 4][slot][lane % 4]
+    double* base;       // &stage[lane / 4][0][lane % 4]
+    __device__ __forceinline__ void jx(int i, int j, double v) const { base[jx_slot(i, j) * 4] = v; }
+    __device__ __forceinline__ void ju(int i, int j, double v) const { base[ju_slot(i, j) * 4] = v; }
 };
 
 // ---- mbarrier / bulk-copy (TMA) helpers, single-CTA scope --------------------------------------------------
@@ -303,22 +305,33 @@ __device__ __forceinline__ void bulk_g2s_evict_last(double* smem_dst, const doub
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
+// shared -> global bulk copy (TMA store): the L2 sees whole lines instead of 8 scattered sectors per warp store.  The
+// scratch is tagged evict_last on the way out and on the way back in; everything that streams through once (inputs,
+// xn, Phi, Gamma) is evict_first, so the streaming output does not push the scratch out of L2.
+__device__ __forceinline__ void bulk_s2g_evict_last(double* gdst, const double* smem_src, unsigned bytes) {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 template <bool ARM, bool RIGID>
-__global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_constant__ SensArgs a) {
+__global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const __grid_constant__ SensArgs a) {
     using C = SfCfg<ARM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* const ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * SF_RING * C::TILE_S;
+    double* const ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::UNION;      // phase B: tile ring
+    double* const stage = ring;                                                               // phase A: staging tile (same memory)
     double* const sxa = reinterpret_cast<double*>(smem_raw + C::SMEM_RING) + (size_t)warp * 29 * 32 + lane;
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_RING + C::SMEM_XA) + warp * SF_RING;
-    const long gw = (long)blockIdx.x * SF_WARPS + warp, nwarps = (long)gridDim.x * SF_WARPS;
+    const long gw = (long)blockIdx.x * C::WARPS + warp, nwarps = (long)gridDim.x * C::WARPS;
     double* const Jw = a.Jw + gw * C::SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
     const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane in phase B
 
-    // zero row of every ring tile (structural zeros of a gathered Jacobian column point at it) and the warp's mbarriers
-    if (lane < 4 * SF_RING) ring[(lane >> 2) * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
+    // the warp's mbarriers (one per ring slot)
     if (lane < SF_RING) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -370,8 +383,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
             for (int c = 0; c < 3; ++c) u[c] = sxa[(26 + c) * 32];
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
-                WarpSink sink{PersistPtr(Jw + ((long)st * 8 + (lane >> 2)) * C::TILE + (lane & 3))};
+                StageSink sink{stage + (lane >> 2) * C::PS + (lane & 3)};
                 model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
+                // the stage tile leaves through the TMA: pass p of the staging tile -> scratch[stage][p], one bulk store per
+                // lane 0..7 (per-lane global stores of these 8-sector rows cost 8 L1 tag cycles each: 100 of phase A's 186 us)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane < 8) bulk_s2g_evict_last(Jw + ((long)st * 8 + lane) * C::TILE, stage + lane * C::PS, C::TILE_BYTES);
                 const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
                 const double an = (st == 2) ? a.h : hh;
 #pragma unroll
@@ -379,14 +397,23 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 1) k_sens_fused(const __grid_co
                     sxa[(13 + c) * 32] = (st == 0) ? k[c] : fma(wgt, k[c], sxa[(13 + c) * 32]);
                     xt[c] = fma(an, k[c], sxa[c * 32]);
                 }
+                // the staging tile may be overwritten once the bulk stores have read it (after the last stage: once
+                // they are complete, because phase B reads the scratch back)
+                if (lane < 8) {
+                    if (st < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
             }
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, sxa[(13 + c) * 32], sxa[c * 32]));
             }
         }
-        asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores above -> async-proxy (bulk copy) reads below
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence_block();
 #endif
+        if (lane < 4) ring[C::TILE + lane] = 0.0;       // zero row of ring slot 0: target of the stage-1 gather's structural zeros
         __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
         prefetch_inputs(g + nwarps);                    // next group's x, u land in shared memory behind phase B
 #ifndef KITE_SF_SKIP_B

@@ -8,10 +8,11 @@ static void go_fused(const SensArgs& a, cudaStream_t s) {
         configured = true;
     }
     const long ngroups = (a.B + 31) / 32;
-    const long want = (ngroups + SF_WARPS - 1) / SF_WARPS;
+    constexpr int W = SfCfg<ARM>::WARPS;
+    const long want = (ngroups + W - 1) / W;
     const long sms = sens_fused_max_warps() / SF_WARPS;
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
-    k_sens_fused<ARM, RIGID><<<grid, SF_WARPS * 32, SfCfg<ARM>::SMEM, s>>>(a);
+    k_sens_fused<ARM, RIGID><<<grid, W * 32, SfCfg<ARM>::SMEM, s>>>(a);
 }
 long sens_fused_max_warps() {
     static long warps = 0;
