@@ -51,8 +51,8 @@ if "colloc" in which:
     c = golden["colloc_nmpc_P5_S2_scaled"]
     rng = np.random.default_rng(0)
     z = torch.from_numpy(np.ascontiguousarray((np.array(c["z"])[None, :] * (1 + 0.01 * rng.standard_normal((B, 209)))).T)).cuda()
-    from oracle.oracle_py import Oracle, params_from_yaml        # only for the constant differentiation matrix
-    compD = Oracle(params_from_yaml(os.path.join(ROOT, "data", "umx_radian.yaml"))).cheb_compdiff(5, 2)
+    from openkite_b200.collocation import comp_diff_matrix
+    compD = comp_diff_matrix(5, 2)
     out = (eng.empty(M * 15, B), eng.empty(M * 225, B), eng.empty(M * 60, B), eng.empty(B))
     ms = timeit(lambda: eng.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], out=out))
     report("colloc_eval G+JX+JU", B, ms, 31600.0, 8.0 * (209 + 165 + 11 * 285))
