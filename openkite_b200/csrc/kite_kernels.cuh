@@ -230,11 +230,14 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 // ================================================================================================
 // RK4 step sensitivities: one persistent kernel, every warp independent (no CTA barrier anywhere).
 //   A warp owns groups of 32 units.  Per group:
-//   phase A (lane = unit):  primal RK4 stages + analytic stage Jacobians, written to the warp's PRIVATE scratch
-//                           Jw[warp][stage][slot][32 units] in global memory.  The region (4 x 111 x 256 B = 114 KB per
-//                           warp, 135 MB for 148 x 8 warps) is rewritten every group and read back within microseconds,
-//                           so it is served from the 126 MB L2 instead of making the 3.5 KB/unit round trip through HBM
-//                           that bounded the earlier two-kernel version (profiles/r1e: HBM-write bound at 5.9 TB/s).
+//   phase A (lane = unit):  primal RK4 stages + analytic stage Jacobians.  Each stage's Jacobians are staged in the warp's
+//                           shared tile [pass = lane / 4][slot][lane % 4] (conflict-free pass stride) and leave as 8 TMA
+//                           bulk stores into the warp's PRIVATE scratch Jw[warp][stage][pass][slot][4 units] in global
+//                           memory.  The region (4 x 111 x 256 B = 114 KB per warp, 101 MB for 148 x 6 warps) is rewritten
+//                           every group and read back within microseconds, so it is served from the 126 MB L2 instead of
+//                           making the 3.5 KB/unit round trip through HBM that bounded the earlier two-kernel version
+//                           (profiles/r1e: HBM-write bound at 5.9 TB/s).  The step state x and the tableau accumulator
+//                           are parked in shared memory, the next group's inputs are prefetched with cp.async.
 //   phase B (8 lanes = unit, 4 units per pass, 8 passes): lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] and runs
 //                           the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers (E = seed [I | 0; 0 | I]).
 //                           The stage tile of the pass ([slot][4 units], 3.5 KB, contiguous in the scratch) is brought
