@@ -80,6 +80,7 @@ struct kite_ctx {
     DevBuf pipe[2];                      // host-pipeline chunk buffers
     DevBuf shared_u, shared_y;
     DevBuf node_w;                       // collocated-cost node weights
+    DevBuf counters;                     // dynamic work counters of the persistent kernels
     nccl_comm_t comm = nullptr;
     int nranks = 1, rank = 0;
 };
@@ -120,7 +121,7 @@ int kite_destroy(kite_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
     ctx->small.release(); ctx->scratch.release(); ctx->pipe[0].release(); ctx->pipe[1].release();
-    ctx->shared_u.release(); ctx->shared_y.release(); ctx->node_w.release();
+    ctx->shared_u.release(); ctx->shared_y.release(); ctx->node_w.release(); ctx->counters.release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
@@ -314,15 +315,19 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
 // ---------------------------------------------------------------- sensitivities -------------------
 size_t kite_rk4_sens_work_bytes(long B) {
     if (B <= 0) return 0;
-    // persistent kernel: one private [4][slots][32] region per resident warp, independent of B beyond one wave
-    const long groups = (B + 31) / 32, warps = std::min(groups, sens_fused_max_warps());
-    return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP_MAX * (size_t)warps;
+    // persistent kernel: one private [4 stages][8 passes][slots][4 units] region per RESIDENT warp (groups are claimed
+    // dynamically, so every warp of every launched CTA may need its region), independent of B beyond one wave
+    const long groups = (B + 31) / 32;
+    const long ctas = std::min((groups + SF_WARPS - 1) / SF_WARPS, sens_fused_max_warps() / SF_WARPS);
+    return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP_MAX * (size_t)(ctas * SF_WARPS);
 }
 
 static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, const double* x, const double* u, double* xn,
                           double* Phi, double* Gamma, void* work) {
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
-    SensArgs a{ctx->K, B, ld, h, x, u, xn, Phi, Gamma, (double*)work};
+    if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    CK(cudaMemsetAsync(ctx->counters.ptr, 0, 8, ctx->stream));
+    SensArgs a{ctx->K, B, ld, h, x, u, xn, Phi, Gamma, (double*)work, (unsigned long long*)ctx->counters.ptr};
     (void)ldw;
     launch_sens_fused(a, rigid, ctx->K.has_arm != 0, ctx->stream);
     LAUNCH_CHECK("k_sens_fused");

@@ -252,6 +252,7 @@ struct SensArgs {
     const double* x; const double* u;
     double* xn; double* Phi; double* Gamma;
     double* Jw;     // scratch: [resident warp][4 stages][8 passes][slots][4 units]
+    unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
 };
 
 #ifndef KITE_SF_WARPS
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     double* const stage = ring;                                                               // phase A: staging tile (same memory)
     double* const sxa = reinterpret_cast<double*>(smem_raw + C::SMEM_RING) + (size_t)warp * 29 * 32 + lane;
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_RING + C::SMEM_XA) + warp * SF_RING;
-    const long gw = (long)blockIdx.x * C::WARPS + warp, nwarps = (long)gridDim.x * C::WARPS;
+    const long gw = (long)blockIdx.x * C::WARPS + warp;
     double* const Jw = a.Jw + gw * C::SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
@@ -369,9 +370,17 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
         }
         __pipeline_commit();
     };
-    prefetch_inputs(gw);
+    // Groups are claimed from a global counter instead of a fixed stride: with 6 warps on 4 schedulers two warps run
+    // alone and faster than the two pairs, and a static split would leave them idle at the end.
+    auto claim_group = [&]() -> long {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
+        return (long)__shfl_sync(0xffffffffu, g, 0);
+    };
+    long g = claim_group();
+    prefetch_inputs(g);
 
-    for (long g = gw; g < ngroups; g += nwarps) {
+    while (g < ngroups) {
         // ---------------- phase A: lane = unit --------------------------------------------------------------
 #ifndef KITE_SF_SKIP_A      // (developer timing switch: skip one phase to profile the other alone; results are garbage)
         {
@@ -418,7 +427,8 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #endif
         if (lane < 4) ring[C::TILE + lane] = 0.0;       // zero row of ring slot 0: target of the stage-1 gather's structural zeros
         __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
-        prefetch_inputs(g + nwarps);                    // next group's x, u land in shared memory behind phase B
+        const long g_next = claim_group();
+        prefetch_inputs(g_next);                        // next group's x, u land in shared memory behind phase B
 #ifndef KITE_SF_SKIP_B
 
         // ---------------- phase B: 8 lanes = unit, 4 units per pass -------------------------------------------
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
         }
 #endif
         __syncwarp();                                   // every lane is done reading the ring before the next group
+        g = g_next;
     }
     __pipeline_wait_prior(0);
 }

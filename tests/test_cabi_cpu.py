@@ -66,12 +66,12 @@ def test_no_cpu_fallback(lib, yaml_path):
 
 
 def test_work_size_queries(lib):
-    # fused sensitivity kernel: one private [4 stages][132 slots][32 units] region per resident warp, one warp per
-    # 32 units, capped at the number of warps the persistent grid runs (device dependent; 256 SMs x 8 without a device)
+    # sensitivity kernel: one private [4 stages][132 slots][32 units] region per resident warp of the persistent grid
+    # (6 warps per CTA, one CTA per 6 groups of 32 units, capped at the SM count; 256 SMs assumed without a device)
     per_warp = 8 * 4 * 132 * 32
-    assert lib.kite_rk4_sens_work_bytes(10) == per_warp
-    assert lib.kite_rk4_sens_work_bytes(33) == 2 * per_warp
+    assert lib.kite_rk4_sens_work_bytes(10) == 6 * per_warp
+    assert lib.kite_rk4_sens_work_bytes(32 * 6 + 1) == 12 * per_warp
     big = lib.kite_rk4_sens_work_bytes(1 << 24)
-    assert big % per_warp == 0 and 8 <= big // per_warp <= 256 * 8
+    assert big % (6 * per_warp) == 0 and 8 <= big // per_warp <= 256 * 8
     assert lib.kite_ekf_work_bytes(10) == 0          # EKF predict keeps the Jacobian in shared memory
     assert lib.kite_rk4_sens_work_bytes(0) == 0

@@ -262,6 +262,25 @@ def test_padded_leading_dimension(eng, okb, oracle):
     assert_close(aos(xf[:, :B]), oracle.rollout(x, u, 25, 1e-3), RTOL, what="rollout ld>B")
 
 
+def test_sens_scratch_stays_inside_work_bytes(eng, oracle):
+    """kite_rk4_sens_work_bytes(B) must cover every resident warp of the persistent kernel (groups are claimed
+    dynamically): guard words behind the workspace stay untouched for small and ragged batches, repeatedly."""
+    import ctypes as C
+    for B in (1, 33, 77, 200, 6 * 32 + 5):
+        nbytes = eng.L.kite_rk4_sens_work_bytes(B)
+        buf = torch.full((nbytes // 8 + 4096,), -3.0, dtype=torch.float64, device="cuda")
+        x = oracle.synth_x0(11, B); u = oracle.synth_controls(11, B, 1)[:, 0, :]
+        xd, ud = soa(x), soa(u)
+        rxn, rPhi, rGam = oracle.rk4_sens(x, u, 0.01)
+        for _ in range(8):
+            xn, Phi, Gam = eng.empty(13, B), eng.empty(169, B), eng.empty(39, B)
+            p = lambda t: C.c_void_p(t.data_ptr())
+            eng._use_torch_stream()
+            eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, B, B, 0.01, p(xd), p(ud), p(xn), p(Phi), p(Gam), p(buf)))
+            assert float((buf[nbytes // 8:] + 3.0).abs().max()) == 0.0, "scratch overrun"
+            assert_close(aos(Phi, 13, 13), rPhi, RTOL, what="Phi B=%d" % B)
+
+
 def test_sens_linearity_property(eng, oracle):
     """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
     B, h = 2048, 0.02
