@@ -438,7 +438,10 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     CK(cudaSetDevice(ctx->device));
     if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemcpyAsync(ctx->small.ptr, W_h, sizeof(double) * 169, cudaMemcpyHostToDevice, ctx->stream));
-    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr};
+    if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    CK(cudaMemsetAsync((char*)ctx->counters.ptr + 8, 0, 8, ctx->stream));
+    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
+              (unsigned long long*)((char*)ctx->counters.ptr + 8)};
     launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, ctx->stream);
     LAUNCH_CHECK("k_ekf_predict");
     return KITE_OK;

@@ -529,6 +529,7 @@ struct EkfArgs {
     const double* x; const double* u; const double* P;
     double* xn; double* Pn;
     const double* W;         // device [169]
+    unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
 };
 template <bool ARM> struct EfCfg {
     static constexpr int WARPS = ARM ? 5 : 6;                         // shared memory bound: 35 / 40 KB per warp
@@ -575,7 +576,6 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
     double* const Jt = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::PER_WARP;
     double* const Qt = Jt + 8 * C::PS;
     double* const Ws = Qt + C::QS;                 // the warp's copy of W (13 x 13 row-major)
-    const long gw = (long)blockIdx.x * C::WARPS + warp, nwarps = (long)gridDim.x * C::WARPS;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
     const int r0 = 2 * l, r1 = 2 * l + 1;          // rows of P (phase B, first product) = columns of Pn (second product)
@@ -593,7 +593,13 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
         }
     };
 
-    for (long g = gw; g < ngroups; g += nwarps) {
+    // groups are claimed from a global counter: 6 warps sit on 4 schedulers and do not all run at the same speed
+    auto claim_group = [&]() -> long {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
+        return (long)__shfl_sync(0xffffffffu, g, 0);
+    };
+    for (long g = claim_group(); g < ngroups; g = claim_group()) {
         double pn0[13], pn1[13];
         load_rows(g, 0, pn0, pn1);                  // first pass's rows of P land behind phase A
         // ---------------- phase A: lane = filter ------------------------------------------------------------
