@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 //                           the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers (E = seed [I | 0; 0 | I]).
 //                           The stage tile of the pass ([slot][4 units], 3.5 KB, contiguous in the scratch) is brought
 //                           L2 -> shared by ONE bulk copy (TMA, cp.async.bulk + mbarrier) per tile into a warp-private
-//                           4-deep ring, read back as conflict-free broadcast LDS with immediate offsets, and
+//                           8-deep ring, read back as conflict-free broadcast LDS with immediate offsets, and
 //                           [Phi | Gamma] leaves straight from registers as full 32 B sectors (4 consecutive units per row).
 // ================================================================================================
 struct SensArgs {
@@ -259,7 +259,7 @@ struct SensArgs {
 #define KITE_SF_WARPS 6                        // measured 5..8 on B200 (profiles/r1m): 6 warps = 101 MB of scratch stay L2 resident
 #endif
 constexpr int SF_WARPS = KITE_SF_WARPS;        // warps per CTA (one CTA per SM): scratch footprint = SMs x warps x 114 KB
-constexpr int SF_RING = 4;                     // stage tiles in flight per warp
+constexpr int SF_RING = 8;                     // ring of stage tiles per warp (7 in flight); fits in the memory phase A uses for staging
 template <bool ARM> struct SfCfg {
     static constexpr int WARPS = ARM ? (SF_WARPS < 5 ? SF_WARPS : 5) : SF_WARPS;   // shared memory: 36 / 42 KB per warp
     static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;      // slots a stage Jacobian occupies
@@ -353,9 +353,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     // tile t = pass * 4 + stage of the current group -> ring slot t % 4 = stage: ONE bulk copy of 3.5 KB issued by lane 0
     auto issue = [&](int t) {
         if (lane == 0 && t < 32) {
-            const int st = t & 3;
-            mbar_expect_tx(bars + st, C::TILE_BYTES);
-            bulk_g2s_evict_last(ring + st * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES, bars + st);
+            const int st = t & 3, slot = t % SF_RING;
+            mbar_expect_tx(bars + slot, C::TILE_BYTES);
+            bulk_g2s_evict_last(ring + slot * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES, bars + slot);
         }
     };
     // inputs of a group -> the warp's shared columns x[13][32] (rows 0..12) and u[3][32] (rows 26..28), asynchronously
@@ -425,7 +425,8 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __threadfence_block();
 #endif
-        if (lane < 4) ring[C::TILE + lane] = 0.0;       // zero row of ring slot 0: target of the stage-1 gather's structural zeros
+        // zero rows of the ring slots that receive stage-1 tiles (slots 0 and 4): targets of the gather's structural zeros
+        if (lane < 8) ring[(lane >> 2) * 4 * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
         __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
         const long g_next = claim_group();
         prefetch_inputs(g_next);                        // next group's x, u land in shared memory behind phase B
@@ -440,13 +441,14 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
             const long unit = g * 32 + p * 4 + lu;
-            const unsigned par = p & 1;                 // each ring slot completes once per pass, 8 (even) times per group
+            const int s0 = (p & 1) * 4;                 // ring slot of tile 4 p + st is s0 + st
+            const unsigned par = (p >> 1) & 1;          // each slot completes once per two passes, 4 (even) times per group
             // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
             __syncwarp();                               // all lanes are past the previous tile: its ring slot is free
             issue(p * 4 + SF_RING - 1);
-            mbar_wait(bars + 0, par);
+            mbar_wait(bars + s0, par);
             {
-                const double* __restrict__ T = ring + lu;
+                const double* __restrict__ T = ring + s0 * C::TILE_S + lu;
                 // keep the packed indices opaque so that the 26 unpacked offsets are not hoisted into registers
 #pragma unroll
                 for (int w = 0; w < 4; ++w) asm volatile("" : "+r"(pk0[w]), "+r"(pk1[w]));
@@ -467,8 +469,8 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
             for (int st = 1; st < 4; ++st) {
                 __syncwarp();
                 issue(p * 4 + st + SF_RING - 1);
-                mbar_wait(bars + st, par);
-                const double* __restrict__ T = ring + st * C::TILE_S + lu;   // ring slot = (4 p + st) % 4 = st
+                mbar_wait(bars + s0 + st, par);
+                const double* __restrict__ T = ring + (s0 + st) * C::TILE_S + lu;
 #pragma unroll
                 for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
                 // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
