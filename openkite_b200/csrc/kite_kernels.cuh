@@ -301,12 +301,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "@!p bra WAIT_%=;\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// global -> shared bulk copy (one instruction, no per-lane work), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s_evict_last(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+// global -> shared bulk copy (one instruction, no per-lane work), completion counted in bytes on the mbarrier.  The
+// expect_tx arrival and the copy are PREDICATED on `pred` instead of sitting in a divergent `if (lane == 0)` branch: the
+// warp stays converged (no BSSY / BSYNC / YIELD round trip per tile).
+__device__ __forceinline__ void bulk_g2s_evict_last(bool pred, double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
     unsigned long long pol;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %3;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%1], [%2], %3, [%4], %5;\n\t}"
+        :: "r"((unsigned)pred), "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
 // shared -> global bulk copy (TMA store): the L2 sees whole lines instead of 8 scattered sectors per warp store.  The
@@ -352,11 +358,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     const double h6 = a.h / 6.0, hh = 0.5 * a.h;
     // tile t = pass * 4 + stage of the current group -> ring slot t % 4 = stage: ONE bulk copy of 3.5 KB issued by lane 0
     auto issue = [&](int t) {
-        if (lane == 0 && t < 32) {
-            const int st = t & 3, slot = t % SF_RING;
-            mbar_expect_tx(bars + slot, C::TILE_BYTES);
-            bulk_g2s_evict_last(ring + slot * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES, bars + slot);
-        }
+        const int st = t & 3, slot = t % SF_RING;
+        bulk_g2s_evict_last(lane == 0 && t < 32, ring + slot * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES,
+                            bars + slot);
     };
     // inputs of a group -> the warp's shared columns x[13][32] (rows 0..12) and u[3][32] (rows 26..28), asynchronously
     auto prefetch_inputs = [&](long g) {
