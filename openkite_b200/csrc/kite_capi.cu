@@ -315,11 +315,12 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
 // ---------------------------------------------------------------- sensitivities -------------------
 size_t kite_rk4_sens_work_bytes(long B) {
     if (B <= 0) return 0;
-    // persistent kernel: one private [4 stages][8 passes][slots][4 units] region per RESIDENT warp (groups are claimed
-    // dynamically, so every warp of every launched CTA may need its region), independent of B beyond one wave
+    // persistent kernel: one private [4 stages][x(13) | u(3)][32 units] line of stage states per RESIDENT warp (groups are
+    // claimed dynamically, so every warp of every launched CTA may need its line), independent of B beyond one wave.
+    // The stage Jacobians themselves never leave shared memory.
     const long groups = (B + 31) / 32;
-    const long ctas = std::min((groups + SF_WARPS - 1) / SF_WARPS, sens_fused_max_warps() / SF_WARPS);
-    return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP_MAX * (size_t)(ctas * SF_WARPS);
+    const long warps = std::min(groups + SF_WARPS, sens_fused_max_warps());     // covers any warps-per-CTA <= SF_WARPS
+    return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP * (size_t)warps;
 }
 
 static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, const double* x, const double* u, double* xn,

@@ -228,22 +228,23 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 }
 
 // ================================================================================================
-// RK4 step sensitivities: one persistent kernel, every warp independent (no CTA barrier anywhere).
-//   A warp owns groups of 32 units.  Per group:
-//   phase A (lane = unit):  primal RK4 stages + analytic stage Jacobians.  Each stage's Jacobians are staged in the warp's
-//                           shared tile [pass = lane / 4][slot][lane % 4] (conflict-free pass stride) and leave as 8 TMA
-//                           bulk stores into the warp's PRIVATE scratch Jw[warp][stage][pass][slot][4 units] in global
-//                           memory.  The region (4 x 111 x 256 B = 114 KB per warp, 101 MB for 148 x 6 warps) is rewritten
-//                           every group and read back within microseconds, so it is served from the 126 MB L2 instead of
-//                           making the 3.5 KB/unit round trip through HBM that bounded the earlier two-kernel version
-//                           (profiles/r1e: HBM-write bound at 5.9 TB/s).  The step state x and the tableau accumulator
-//                           are parked in shared memory, the next group's inputs are prefetched with cp.async.
-//   phase B (8 lanes = unit, 4 units per pass, 8 passes): lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] and runs
-//                           the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers (E = seed [I | 0; 0 | I]).
-//                           The stage tile of the pass ([slot][4 units], 3.5 KB, contiguous in the scratch) is brought
-//                           L2 -> shared by ONE bulk copy (TMA, cp.async.bulk + mbarrier) per tile into a warp-private
-//                           8-deep ring, read back as conflict-free broadcast LDS with immediate offsets, and
-//                           [Phi | Gamma] leaves straight from registers as full 32 B sectors (4 consecutive units per row).
+// RK4 step sensitivities: one persistent kernel, every warp independent (no CTA barrier anywhere), the stage Jacobians
+// never leave the SM.  A warp owns groups of 32 units, claimed from a global counter.  Per group:
+//   step 1 (lane = unit, 32 units): the primal RK4 step (RHS only, few registers).  xn leaves; the four stage states and
+//                           the control are parked in the warp's private 16 KB line of global scratch (L2 resident).
+//   then four rounds of 8 units each:
+//   step 2 (lane = (unit, STAGE): 8 units x 4 stages): the four stage Jacobians of a unit are independent once the stage
+//                           states are known, so ONE pass of the analytic Jacobian code evaluates all four stages of
+//                           8 units.  That is what shrinks the Jacobians in flight from 32 units x 4 stages = 114 KB per
+//                           warp (an L2 / HBM round trip in the earlier version: 3.7 GB of write-back per 1 M units) to
+//                           8 units x 4 stages = 27 KB: they stay in the warp's SHARED-memory tile
+//                           [stage][pass][slot][4 units], written conflict free straight from the Jacobian code.
+//   phase B (8 lanes = unit, 4 units per pass, 2 passes): lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] and
+//                           runs the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers
+//                           (E = seed [I | 0; 0 | I]); stage 1 is a pure gather of two Jacobian columns.  Jacobian
+//                           entries are conflict-free broadcast LDS.64 with immediate offsets; [Phi | Gamma] leaves
+//                           straight from registers as full 32 B sectors (4 consecutive units per row).
+//   No TMA, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
 // ================================================================================================
 struct SensArgs {
     KiteConsts K;
@@ -251,272 +252,236 @@ struct SensArgs {
     double h;
     const double* x; const double* u;
     double* xn; double* Phi; double* Gamma;
-    double* Jw;     // scratch: [resident warp][4 stages][8 passes][slots][4 units]
+    double* Sw;     // scratch: [resident warp][4 stages][16 = x(13) | u(3)][32 units]
     unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
 };
 
+// ---- compact slots of the sensitivity tile ------------------------------------------------------------------
+// As SLOT_TAB, but the 12 entries d q_dot / d w = {+-q/2} (kite_model.cuh, Qw) that repeat a value WITH ITS SIGN share a
+// slot (12 -> 7): 106 slots without a tether arm (127 with), so that eight warps' tiles fit one SM's shared memory.
+struct SensTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
+constexpr int SENS_SLOTS_NOARM = JAC_SLOTS_NOARM - 5, SENS_SLOTS = JAC_SLOTS - 5;
+constexpr SensTab make_sens_tab() {
+    SensTab t{};
+    // value id of Qw[i][j]: +-1 = +-a0/2, +-2 = +-a1/2, +-3 = +-a2/2, 4 = s/2
+    const int qw[4][3] = {{-1, -2, -3}, {4, -3, 2}, {3, 4, -1}, {-2, 1, 4}};
+    int s = 0;
+    for (int i = 0; i < 13; ++i)
+        for (int j = 0; j < 13; ++j) {
+            t.jx[i][j] = -1;
+            if (!jx_nz(i, j, false)) continue;
+            if (i >= 9 && j >= 3 && j < 6) {
+                int found = -1;
+                for (int i2 = 9; i2 <= i && found < 0; ++i2)
+                    for (int j2 = 3; j2 < 6 && found < 0; ++j2)
+                        if ((i2 < i || j2 < j) && qw[i2 - 9][j2 - 3] == qw[i - 9][j - 3]) found = t.jx[i2][j2];
+                if (found >= 0) { t.jx[i][j] = found; continue; }
+            }
+            t.jx[i][j] = s++;
+        }
+    for (int i = 0; i < 13; ++i)
+        for (int j = 0; j < 3; ++j) t.ju[i][j] = ju_nz(i, j) ? s++ : -1;
+    for (int i = 0; i < 13; ++i)
+        for (int j = 0; j < 13; ++j)
+            if (jx_nz(i, j, true) && !jx_nz(i, j, false)) t.jx[i][j] = s++;
+    for (int i = 0; i < 13; ++i)
+        for (int c = 0; c < 16; ++c) t.col[i][c] = (c < 13) ? t.jx[i][c] : t.ju[i][c - 13];
+    return t;
+}
+__device__ constexpr SensTab SENS_TAB = make_sens_tab();
+static_assert(make_sens_tab().ju[5][2] == SENS_SLOTS_NOARM - 1, "sens slot numbering");
+static_assert(make_sens_tab().jx[5][12] == SENS_SLOTS - 1, "sens slot numbering");
+static_assert(make_sens_tab().jx[10][3] == make_sens_tab().jx[12][5] && make_sens_tab().jx[9][3] == make_sens_tab().jx[11][5],
+              "shared quaternion-rate slots");
+
 #ifndef KITE_SF_WARPS
-#define KITE_SF_WARPS 6                        // measured 5..8 on B200 (profiles/r1m): 6 warps = 101 MB of scratch stay L2 resident
+#define KITE_SF_WARPS 8                        // 8 warps x 255 registers = the whole register file, 2 warps per scheduler
 #endif
-constexpr int SF_WARPS = KITE_SF_WARPS;        // warps per CTA (one CTA per SM): scratch footprint = SMs x warps x 114 KB
-constexpr int SF_RING = 8;                     // ring of stage tiles per warp (7 in flight); fits in the memory phase A uses for staging
+constexpr int SF_WARPS = KITE_SF_WARPS;        // upper bound of warps per CTA (one CTA per SM)
+constexpr size_t SF_SMEM_MAX = 227 * 1024;
+constexpr long SF_SCRATCH_PER_WARP = 4L * 16 * 32;      // doubles: [stage][x(13) | u(3)][32 units]
 template <bool ARM> struct SfCfg {
-    static constexpr int WARPS = ARM ? (SF_WARPS < 5 ? SF_WARPS : 5) : SF_WARPS;   // shared memory: 36 / 42 KB per warp
-    static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;      // slots a stage Jacobian occupies
-    static constexpr int TILE = NS * 4;                               // doubles per tile: [slot][4 units], contiguous in scratch
-    static constexpr int TILE_S = TILE + 4;                           // shared-memory tile: + one zero row (gather target)
-    static constexpr unsigned TILE_BYTES = TILE * 8;                  // one bulk copy (multiple of 16)
-    static constexpr long SCRATCH_PER_WARP = 4L * 8 * TILE;           // doubles: [stage][pass][slot][4]
-    // phase-A staging tile of one stage, [pass][slot][4 units] with the pass stride == 4 (mod 16) doubles so that the
-    // 8 four-lane groups of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
-    static constexpr int PS = TILE + (TILE % 16 == 12 ? 8 : (TILE % 16 == 0 ? 4 : (20 - TILE % 16) % 16));
-    // per-warp shared memory: staging (phase A) and the tile ring (phase B) share one region; + x[13], acc[13], u[3] columns
-    static constexpr int UNION = (8 * PS > SF_RING * TILE_S) ? 8 * PS : SF_RING * TILE_S;
-    static constexpr size_t SMEM_RING = sizeof(double) * WARPS * UNION;
-    static constexpr size_t SMEM_XA = sizeof(double) * WARPS * 29 * 32;
-    static constexpr size_t SMEM = SMEM_RING + SMEM_XA + sizeof(unsigned long long) * WARPS * SF_RING;
+    static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM;    // slots a stage Jacobian occupies
+    static constexpr int TILE = NS * 4;                               // doubles per tile: [slot][4 units]
+    // tile stride: + one zero row (target of the gather's structural zeros), and == 4 (mod 16) doubles so that the 8
+    // four-lane groups (stage, pass) of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
+    static constexpr int TILE_S = TILE + 4 + ((4 - (TILE + 4) % 16) + 16) % 16;
+    static constexpr size_t SMEM_PER_WARP = sizeof(double) * 8 * TILE_S;          // [4 stages][2 passes] tiles
+    static constexpr int FIT = (int)(SF_SMEM_MAX / SMEM_PER_WARP);
+    static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
+    static constexpr size_t SMEM = SMEM_PER_WARP * WARPS;
 };
-static_assert(SfCfg<false>::PS % 16 == 4 && SfCfg<true>::PS % 16 == 4 && SfCfg<false>::PS % 2 == 0, "staging pass stride");
-constexpr long SF_SCRATCH_PER_WARP_MAX = 4L * 8 * JAC_SLOTS * 4;
+static_assert(SfCfg<false>::TILE_S % 16 == 4 && SfCfg<true>::TILE_S % 16 == 4, "tile stride");
+static_assert(SfCfg<false>::TILE_S >= SfCfg<false>::TILE + 4 && SfCfg<true>::TILE_S >= SfCfg<true>::TILE + 4, "zero row");
 
-struct StageSink {      // phase-A staging tile of the warp: compact slots of this lane's unit at [lane / 4][slot][lane % 4]
-    double* base;       // &stage[lane / 4][0][lane % 4]
-    __device__ __forceinline__ void jx(int i, int j, double v) const { base[jx_slot(i, j) * 4] = v; }
-    __device__ __forceinline__ void ju(int i, int j, double v) const { base[ju_slot(i, j) * 4] = v; }
+struct StageSink {      // the warp's tile: compact slots of this lane's (unit, stage) at [stage][unit / 4][slot][unit % 4]
+    double* base;
+    __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 4] = v; }
+    __device__ __forceinline__ void ju(int i, int j, double v) const { base[SENS_TAB.ju[i][j] * 4] = v; }
 };
-
-// ---- mbarrier / bulk-copy (TMA) helpers, single-CTA scope --------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}"
-        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (one instruction, no per-lane work), completion counted in bytes on the mbarrier.  The
-// expect_tx arrival and the copy are PREDICATED on `pred` instead of sitting in a divergent `if (lane == 0)` branch: the
-// warp stays converged (no BSSY / BSYNC / YIELD round trip per tile).
-__device__ __forceinline__ void bulk_g2s_evict_last(bool pred, double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
-    unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.u32 p, %0, 0;\n\t"
-        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %3;\n\t"
-        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%1], [%2], %3, [%4], %5;\n\t}"
-        :: "r"((unsigned)pred), "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-
-// shared -> global bulk copy (TMA store): the L2 sees whole lines instead of 8 scattered sectors per warp store.  The
-// scratch is tagged evict_last on the way out and on the way back in; everything that streams through once (inputs,
-// xn, Phi, Gamma) is evict_first, so the streaming output does not push the scratch out of L2.
-__device__ __forceinline__ void bulk_s2g_evict_last(double* gdst, const double* smem_src, unsigned bytes) {
-    unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
 
 template <bool ARM, bool RIGID>
 __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const __grid_constant__ SensArgs a) {
     using C = SfCfg<ARM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* const ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::UNION;      // phase B: tile ring
-    double* const stage = ring;                                                               // phase A: staging tile (same memory)
-    double* const sxa = reinterpret_cast<double*>(smem_raw + C::SMEM_RING) + (size_t)warp * 29 * 32 + lane;
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_RING + C::SMEM_XA) + warp * SF_RING;
-    const long gw = (long)blockIdx.x * C::WARPS + warp;
-    double* const Jw = a.Jw + gw * C::SCRATCH_PER_WARP;
+    double* const tile = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 8 * C::TILE_S;
+    double* const Sw = a.Sw + ((long)blockIdx.x * C::WARPS + warp) * SF_SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
     const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane in phase B
 
-    // the warp's mbarriers (one per ring slot)
-    if (lane < SF_RING) mbar_init(bars + lane, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
+    // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
+    if (lane < 8) tile[(lane >> 2) * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
     // per-lane slot indices of Jacobian columns c0, c1 (13 rows each), one byte per row; NS = the zero row
     unsigned pk0[4] = {0, 0, 0, 0}, pk1[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
-        int s0 = SLOT_TAB.col[i][c0], s1 = SLOT_TAB.col[i][c1];
+        int s0 = SENS_TAB.col[i][c0], s1 = SENS_TAB.col[i][c1];
         if (s0 < 0 || s0 >= C::NS || (RIGID && (i < 6 || c0 >= 13))) s0 = C::NS;
         if (s1 < 0 || s1 >= C::NS || (RIGID && (i < 6 || c1 >= 13))) s1 = C::NS;
         pk0[i >> 2] |= (unsigned)s0 << (8 * (i & 3));
         pk1[i >> 2] |= (unsigned)s1 << (8 * (i & 3));
     }
     const double h6 = a.h / 6.0, hh = 0.5 * a.h;
-    // tile t = pass * 4 + stage of the current group -> ring slot t % 4 = stage: ONE bulk copy of 3.5 KB issued by lane 0
-    auto issue = [&](int t) {
-        const int st = t & 3, slot = t % SF_RING;
-        bulk_g2s_evict_last(lane == 0 && t < 32, ring + slot * C::TILE_S, Jw + ((long)st * 8 + (t >> 2)) * C::TILE, C::TILE_BYTES,
-                            bars + slot);
-    };
-    // inputs of a group -> the warp's shared columns x[13][32] (rows 0..12) and u[3][32] (rows 26..28), asynchronously
-    auto prefetch_inputs = [&](long g) {
-        if (g < ngroups) {
-            const long unit = g * 32 + lane;
-            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last unit, store nothing
-#pragma unroll
-            for (int c = 0; c < 13; ++c) __pipeline_memcpy_async(sxa + c * 32, a.x + (long)c * a.ld + ui, 8);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) __pipeline_memcpy_async(sxa + (26 + c) * 32, a.u + (long)c * a.ld + ui, 8);
-        }
-        __pipeline_commit();
-    };
-    // Groups are claimed from a global counter instead of a fixed stride: with 6 warps on 4 schedulers two warps run
-    // alone and faster than the two pairs, and a static split would leave them idle at the end.
+    // Groups are claimed from a global counter instead of a fixed stride: warps that share a scheduler run at different
+    // speeds, and a static split would leave the fast ones idle at the end.  The next group's input lines are pulled
+    // into L2 while this one is computed (register free).
     auto claim_group = [&]() -> long {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
-        return (long)__shfl_sync(0xffffffffu, g, 0);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if ((long)g < ngroups) {
+            const long first = (long)g * 32;
+            const int row = lane >> 1;                                  // 13 rows of x, 3 of u, 2 x 128 B each
+            const double* p = (row < 13 ? a.x + (long)row * a.ld : a.u + (long)(row - 13) * a.ld) + first + (lane & 1) * 16;
+            if (first + (lane & 1) * 16 < a.B) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+        }
+        return (long)g;
     };
     long g = claim_group();
-    prefetch_inputs(g);
+    __syncwarp();
 
     while (g < ngroups) {
-        // ---------------- phase A: lane = unit --------------------------------------------------------------
-#ifndef KITE_SF_SKIP_A      // (developer timing switch: skip one phase to profile the other alone; results are garbage)
+        const long g_next = claim_group();
+        // ---------------- step 1: lane = unit, primal RK4 step -------------------------------------------------
         {
             const long unit = g * 32 + lane;
-            // the step base state and the tableau accumulator are parked in shared memory ([13][32] columns): the
-            // Jacobian code needs every register (profiles/r1j: spill loads on the critical path were 60% of phase A)
-            double u[3], k[13], xt[13];
-            __pipeline_wait_prior(0);                   // this lane's inputs (prefetched during the previous phase B)
+            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last unit, store nothing
+            double x[13], u[3], k[13], xt[13], acc[13];
 #pragma unroll
-            for (int c = 0; c < 13; ++c) xt[c] = sxa[c * 32];
+            for (int c = 0; c < 13; ++c) { x[c] = __ldcs(a.x + (long)c * a.ld + ui); xt[c] = x[c]; }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) u[c] = sxa[(26 + c) * 32];
+            for (int c = 0; c < 3; ++c) { u[c] = RIGID ? 0.0 : __ldcs(a.u + (long)c * a.ld + ui); __stcg(Sw + (13 + c) * 32 + lane, u[c]); }
+            NoSink ns;
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
-                StageSink sink{stage + (lane >> 2) * C::PS + (lane & 3)};
-                model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
-                // the stage tile leaves through the TMA: pass p of the staging tile -> scratch[stage][p], one bulk store per
-                // lane 0..7 (per-lane global stores of these 8-sector rows cost 8 L1 tag cycles each: 100 of phase A's 186 us)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane < 8) bulk_s2g_evict_last(Jw + ((long)st * 8 + lane) * C::TILE, stage + lane * C::PS, C::TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < 13; ++c) __stcg(Sw + (st * 16 + c) * 32 + lane, xt[c]);
+                model_eval<RIGID, false>(a.K, a.K.A, xt, u, k, ns);
                 const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
                 const double an = (st == 2) ? a.h : hh;
 #pragma unroll
                 for (int c = 0; c < 13; ++c) {
-                    sxa[(13 + c) * 32] = (st == 0) ? k[c] : fma(wgt, k[c], sxa[(13 + c) * 32]);
-                    xt[c] = fma(an, k[c], sxa[c * 32]);
+                    acc[c] = (st == 0) ? k[c] : fma(wgt, k[c], acc[c]);
+                    xt[c] = fma(an, k[c], x[c]);
                 }
-                // the staging tile may be overwritten once the bulk stores have read it (after the last stage: once
-                // they are complete, because phase B reads the scratch back)
-                if (lane < 8) {
-                    if (st < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                }
-                __syncwarp();
             }
             if (unit < a.B) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, sxa[(13 + c) * 32], sxa[c * 32]));
+                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, acc[c], x[c]));
             }
         }
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __threadfence_block();
-#endif
-        // zero rows of the ring slots that receive stage-1 tiles (slots 0 and 4): targets of the gather's structural zeros
-        if (lane < 8) ring[(lane >> 2) * 4 * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
-        __syncwarp();                                   // the warp's scratch is complete and visible to all its lanes
-        const long g_next = claim_group();
-        prefetch_inputs(g_next);                        // next group's x, u land in shared memory behind phase B
-#ifndef KITE_SF_SKIP_B
+        __syncwarp();                                   // the stage states of all 32 units are visible to the warp
 
-        // ---------------- phase B: 8 lanes = unit, 4 units per pass -------------------------------------------
 #pragma unroll 1
-        for (int t = 0; t < SF_RING - 1; ++t) issue(t);
-        double D[2][16], N0[13], N1[13], A0[13], A1[13];   // D[.][13..15]: the control part of the seed (constant)
-#pragma unroll
-        for (int m = 13; m < 16; ++m) { D[0][m] = (m == c0) ? 1.0 : 0.0; D[1][m] = (m == c1) ? 1.0 : 0.0; }
-#pragma unroll 1
-        for (int p = 0; p < 8; ++p) {
-            const long unit = g * 32 + p * 4 + lu;
-            const int s0 = (p & 1) * 4;                 // ring slot of tile 4 p + st is s0 + st
-            const unsigned par = (p >> 1) & 1;          // each slot completes once per two passes, 4 (even) times per group
-            // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
-            __syncwarp();                               // all lanes are past the previous tile: its ring slot is free
-            issue(p * 4 + SF_RING - 1);
-            mbar_wait(bars + s0, par);
+        for (int r = 0; r < 4; ++r) {
+            // ---------------- step 2: lane = (unit, stage), four stage Jacobians of 8 units -> shared tile ----------
+#ifndef KITE_SF_SKIP_A      // (developer timing switch: skip one phase to profile the other alone; results are garbage)
             {
-                const double* __restrict__ T = ring + s0 * C::TILE_S + lu;
-                // keep the packed indices opaque so that the 26 unpacked offsets are not hoisted into registers
+                const int u8 = lane & 7, s = lane >> 3;
+                double xt[13], u[3], k[13];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) asm volatile("" : "+r"(pk0[w]), "+r"(pk1[w]));
+                for (int c = 0; c < 13; ++c) xt[c] = __ldcg(Sw + (s * 16 + c) * 32 + r * 8 + u8);
 #pragma unroll
-                for (int i = 0; i < 13; ++i) {
-                    N0[i] = T[((pk0[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
-                    N1[i] = T[((pk1[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
-                }
-#pragma unroll
-                for (int i = 0; i < 13; ++i) {
-                    A0[i] = N0[i]; A1[i] = N1[i];
-                    D[0][i] = fma(hh, N0[i], (i == c0) ? 1.0 : 0.0);
-                    D[1][i] = fma(hh, N1[i], (i == c1) ? 1.0 : 0.0);
-                }
+                for (int c = 0; c < 3; ++c) u[c] = __ldcg(Sw + (13 + c) * 32 + r * 8 + u8);
+                StageSink sink{tile + (s * 2 + (u8 >> 2)) * C::TILE_S + (u8 & 3)};
+                model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
             }
-            // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled: instruction-cache footprint)
+#endif
+            __syncwarp();                               // the tile is complete and visible to all lanes
+#ifndef KITE_SF_SKIP_B
+            // ---------------- phase B: 8 lanes = unit, 4 units per pass ---------------------------------------------
+            double D[2][16], N0[13], N1[13], A0[13], A1[13];   // D[.][13..15]: the control part of the seed (constant)
+#pragma unroll
+            for (int m = 13; m < 16; ++m) { D[0][m] = (m == c0) ? 1.0 : 0.0; D[1][m] = (m == c1) ? 1.0 : 0.0; }
 #pragma unroll 1
-            for (int st = 1; st < 4; ++st) {
-                __syncwarp();
-                issue(p * 4 + st + SF_RING - 1);
-                mbar_wait(bars + s0 + st, par);
-                const double* __restrict__ T = ring + (s0 + st) * C::TILE_S + lu;
+            for (int p = 0; p < 2; ++p) {
+                const long unit = g * 32 + r * 8 + p * 4 + lu;
+                // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
+                {
+                    const double* __restrict__ T = tile + p * C::TILE_S + lu;
+                    // keep the packed indices opaque so that the 26 unpacked offsets are not hoisted into registers
 #pragma unroll
-                for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
-                // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
-                // N[i][.], so consecutive DFMAs never depend on each other; columns 13..15 are the control seed
+                    for (int w = 0; w < 4; ++w) asm volatile("" : "+r"(pk0[w]), "+r"(pk1[w]));
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                    for (int i = 0; i < 13; ++i) {
+                        N0[i] = T[((pk0[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
+                        N1[i] = T[((pk1[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
+                    }
 #pragma unroll
-                    for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
-                        if ((j < 13) ? jx_nz(i, j, ARM) : (!RIGID && ju_nz(i, j - 13))) {
-                            const double jv = T[SLOT_TAB.col[i][j] * 4];     // broadcast LDS.64, immediate offset
-                            N0[i] = fma(jv, D[0][j], N0[i]);
-                            N1[i] = fma(jv, D[1][j], N1[i]);
-                        }
+                    for (int i = 0; i < 13; ++i) {
+                        A0[i] = N0[i]; A1[i] = N1[i];
+                        D[0][i] = fma(hh, N0[i], (i == c0) ? 1.0 : 0.0);
+                        D[1][i] = fma(hh, N1[i], (i == c1) ? 1.0 : 0.0);
                     }
                 }
-                const double wgt = (st == 3) ? 1.0 : 2.0;
-                const double an = (st == 2) ? a.h : hh;
+                // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled: instruction-cache footprint)
+#pragma unroll 1
+                for (int st = 1; st < 4; ++st) {
+                    const double* __restrict__ T = tile + (st * 2 + p) * C::TILE_S + lu;
 #pragma unroll
-                for (int i = 0; i < 13; ++i) {
-                    A0[i] = fma(wgt, N0[i], A0[i]);
-                    A1[i] = fma(wgt, N1[i], A1[i]);
-                    D[0][i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);   // unused after the last stage
-                    D[1][i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                    for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
+                    // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
+                    // N[i][.], so consecutive DFMAs never depend on each other; columns 13..15 are the control seed
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                        for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
+                            if ((j < 13) ? jx_nz(i, j, ARM) : (!RIGID && ju_nz(i, j - 13))) {
+                                const double jv = T[SENS_TAB.col[i][j] * 4];     // broadcast LDS.64, immediate offset
+                                N0[i] = fma(jv, D[0][j], N0[i]);
+                                N1[i] = fma(jv, D[1][j], N1[i]);
+                            }
+                        }
+                    }
+                    const double wgt = (st == 3) ? 1.0 : 2.0;
+                    const double an = (st == 2) ? a.h : hh;
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        A0[i] = fma(wgt, N0[i], A0[i]);
+                        A1[i] = fma(wgt, N1[i], A1[i]);
+                        D[0][i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);   // unused after the last stage
+                        D[1][i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                    }
+                }
+                if (unit < a.B) {
+                    // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
+                    double* const o0 = (c0 < 13) ? a.Phi + (long)c0 * a.ld + unit : a.Gamma + (long)(c0 - 13) * a.ld + unit;
+                    double* const o1 = (c1 < 13) ? a.Phi + (long)c1 * a.ld + unit : a.Gamma + (long)(c1 - 13) * a.ld + unit;
+                    const long r0 = (c0 < 13 ? 13 : 3) * a.ld, r1 = (c1 < 13 ? 13 : 3) * a.ld;
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        __stcs(o0 + i * r0, fma(h6, A0[i], (i == c0) ? 1.0 : 0.0));
+                        __stcs(o1 + i * r1, fma(h6, A1[i], (i == c1) ? 1.0 : 0.0));
+                    }
                 }
             }
-            if (unit < a.B) {
-                // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
-                double* const o0 = (c0 < 13) ? a.Phi + (long)c0 * a.ld + unit : a.Gamma + (long)(c0 - 13) * a.ld + unit;
-                double* const o1 = (c1 < 13) ? a.Phi + (long)c1 * a.ld + unit : a.Gamma + (long)(c1 - 13) * a.ld + unit;
-                const long r0 = (c0 < 13 ? 13 : 3) * a.ld, r1 = (c1 < 13 ? 13 : 3) * a.ld;
-#pragma unroll
-                for (int i = 0; i < 13; ++i) {
-                    __stcs(o0 + i * r0, fma(h6, A0[i], (i == c0) ? 1.0 : 0.0));
-                    __stcs(o1 + i * r1, fma(h6, A1[i], (i == c1) ? 1.0 : 0.0));
-                }
-            }
-        }
 #endif
-        __syncwarp();                                   // every lane is done reading the ring before the next group
+            __syncwarp();                               // every lane is done reading the tile before the next round
+        }
         g = g_next;
     }
-    __pipeline_wait_prior(0);
 }
 
 // ================================================================================================
