@@ -307,9 +307,10 @@ template <bool ARM> struct SfCfg {
     // four-lane groups (stage, pass) of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
     static constexpr int TILE_S = TILE + 4 + ((4 - (TILE + 4) % 16) + 16) % 16;
     static constexpr size_t SMEM_PER_WARP = sizeof(double) * 8 * TILE_S;          // [4 stages][2 passes] tiles
-    static constexpr int FIT = (int)(SF_SMEM_MAX / SMEM_PER_WARP);
+    static constexpr int FIT = (int)((SF_SMEM_MAX - 2048) / SMEM_PER_WARP);
     static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
-    static constexpr size_t SMEM = SMEM_PER_WARP * WARPS;
+    static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
+    static constexpr size_t SMEM = SMEM_TILES + sizeof(unsigned) * 13 * 32;       // + gather table
 };
 static_assert(SfCfg<false>::TILE_S % 16 == 4 && SfCfg<true>::TILE_S % 16 == 4, "tile stride");
 static_assert(SfCfg<false>::TILE_S >= SfCfg<false>::TILE + 4 && SfCfg<true>::TILE_S >= SfCfg<true>::TILE + 4, "zero row");
@@ -333,16 +334,24 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 
     // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
     if (lane < 8) tile[(lane >> 2) * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
-    // per-lane slot indices of Jacobian columns c0, c1 (13 rows each), one byte per row; NS = the zero row
-    unsigned pk0[4] = {0, 0, 0, 0}, pk1[4] = {0, 0, 0, 0};
+    // gather table: byte offsets (within a tile, lane's unit included) of the entries of Jacobian columns c0 (low half)
+    // and c1 (high half) of this lane, one word per row; structural zeros point at the zero row.  [13][32 lanes].
+    unsigned* const goff = reinterpret_cast<unsigned*>(smem_raw + C::SMEM_TILES) + lane;
+    if (warp == 0) {
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
-        int s0 = SENS_TAB.col[i][c0], s1 = SENS_TAB.col[i][c1];
-        if (s0 < 0 || s0 >= C::NS || (RIGID && (i < 6 || c0 >= 13))) s0 = C::NS;
-        if (s1 < 0 || s1 >= C::NS || (RIGID && (i < 6 || c1 >= 13))) s1 = C::NS;
-        pk0[i >> 2] |= (unsigned)s0 << (8 * (i & 3));
-        pk1[i >> 2] |= (unsigned)s1 << (8 * (i & 3));
+        for (int i = 0; i < 13; ++i) {
+            int s0 = C::NS, s1 = C::NS;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int sl = SENS_TAB.col[i][c];
+                const bool ok = sl >= 0 && sl < C::NS && !(RIGID && (i < 6 || c >= 13));
+                if (ok && c == c0) s0 = sl;
+                if (ok && c == c1) s1 = sl;
+            }
+            goff[i * 32] = (unsigned)((s0 * 4 + lu) * 8) | ((unsigned)((s1 * 4 + lu) * 8) << 16);
+        }
     }
+    __syncthreads();
     const double h6 = a.h / 6.0, hh = 0.5 * a.h;
     // Groups are claimed from a global counter instead of a fixed stride: warps that share a scheduler run at different
     // speeds, and a static split would leave the fast ones idle at the end.  The next group's input lines are pulled
@@ -420,14 +429,12 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 const long unit = g * 32 + r * 8 + p * 4 + lu;
                 // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
                 {
-                    const double* __restrict__ T = tile + p * C::TILE_S + lu;
-                    // keep the packed indices opaque so that the 26 unpacked offsets are not hoisted into registers
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) asm volatile("" : "+r"(pk0[w]), "+r"(pk1[w]));
+                    const char* const T = reinterpret_cast<const char*>(tile + p * C::TILE_S);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
-                        N0[i] = T[((pk0[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
-                        N1[i] = T[((pk1[i >> 2] >> (8 * (i & 3))) & 0xffu) * 4];
+                        const unsigned o = goff[i * 32];
+                        N0[i] = *reinterpret_cast<const double*>(T + (o & 0xffffu));
+                        N1[i] = *reinterpret_cast<const double*>(T + (o >> 16));
                     }
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
@@ -461,8 +468,13 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                     for (int i = 0; i < 13; ++i) {
                         A0[i] = fma(wgt, N0[i], A0[i]);
                         A1[i] = fma(wgt, N1[i], A1[i]);
-                        D[0][i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);   // unused after the last stage
-                        D[1][i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                    }
+                    if (st < 3) {                                   // (warp-uniform) the last stage feeds no further one
+#pragma unroll
+                        for (int i = 0; i < 13; ++i) {
+                            D[0][i] = fma(an, N0[i], (i == c0) ? 1.0 : 0.0);
+                            D[1][i] = fma(an, N1[i], (i == c1) ? 1.0 : 0.0);
+                        }
                     }
                 }
                 if (unit < a.B) {
@@ -481,279 +493,6 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
             __syncwarp();                               // every lane is done reading the tile before the next round
         }
         g = g_next;
-    }
-}
-
-// ================================================================================================
-// RK4 step sensitivities, warp-specialised (the product path for the kite models): the same arithmetic as k_sens_fused,
-// split over two warp roles with different register budgets (setmaxnreg), so that THREE warps share a scheduler instead
-// of two.  One CTA of 12 warps per SM (persistent):
-//   producers (warps 0..3, 248 registers): step 1 (primal RK4 of a claimed group of 32 units, stage states parked in the
-//             warp's L2-resident scratch line) and step 2 (lane = (unit, stage): the four stage Jacobians of 8 units)
-//             into one of the producer's shared-memory tile buffers [stage][pass][slot pair][2 units][2 slots];
-//   consumers (warps 4..11, 128 registers; warps 4 + w and 8 + w serve producer w, all three on scheduler w): phase B
-//             with 16 lanes = unit, ONE tangent column per lane, two units per pass, two passes of each tile per
-//             consumer.  Slots are numbered column-major and read two at a time (broadcast LDS.128), each value feeding
-//             the DFMAs of all its users.
-//   Hand-over: one full / empty mbarrier pair per tile buffer (generic-proxy stores, release / acquire at CTA scope).
-// ================================================================================================
-constexpr int WS_PRODUCERS = 4, WS_CONSUMERS = 8;
-constexpr int WS_THREADS = (WS_PRODUCERS + WS_CONSUMERS) * 32;     // 384 threads -> 168 registers each at launch
-#ifndef KITE_WS_REGS_PRODUCER
-#define KITE_WS_REGS_PRODUCER 200
-#define KITE_WS_REGS_CONSUMER 152
-#endif
-
-struct WsTab {
-    int slot[13][16];                 // slot of entry (row, tangent column) of [Jx | Ju], -1 = structural zero
-    int nusers[JAC_SLOTS];            // entries that read a slot (the {+-q/2} values of d q_dot / d w repeat, see SensTab)
-    int ui[JAC_SLOTS][3], uj[JAC_SLOTS][3];
-    int ns_noarm, ns;
-};
-constexpr WsTab make_ws_tab() {
-    WsTab t{};
-    const int qw[4][3] = {{-1, -2, -3}, {4, -3, 2}, {3, 4, -1}, {-2, 1, 4}};
-    for (int i = 0; i < 13; ++i)
-        for (int c = 0; c < 16; ++c) t.slot[i][c] = -1;
-    int s = 0;
-    for (int pass = 0; pass < 2; ++pass) {                 // pass 0: entries of every model, pass 1: tether-arm extras
-        for (int c = 0; c < 16; ++c)                       // column-major: consecutive slots belong to different rows
-            for (int i = 0; i < 13; ++i) {
-                const bool nz0 = (c < 13) ? jx_nz(i, c, false) : ju_nz(i, c - 13);
-                const bool nz1 = (c < 13) ? jx_nz(i, c, true) : ju_nz(i, c - 13);
-                if (pass == 0 ? !nz0 : !(nz1 && !nz0)) continue;
-                int found = -1;
-                if (i >= 9 && c >= 3 && c < 6)
-                    for (int c2 = 3; c2 <= c && found < 0; ++c2)
-                        for (int i2 = 9; i2 < 13 && found < 0; ++i2)
-                            if ((c2 < c || i2 < i) && qw[i2 - 9][c2 - 3] == qw[i - 9][c - 3]) found = t.slot[i2][c2];
-                const int sl = found >= 0 ? found : s++;
-                t.slot[i][c] = sl;
-                t.ui[sl][t.nusers[sl]] = i; t.uj[sl][t.nusers[sl]] = c; ++t.nusers[sl];
-            }
-        if (pass == 0) t.ns_noarm = s;
-    }
-    t.ns = s;
-    return t;
-}
-__device__ constexpr WsTab WS_TAB = make_ws_tab();
-static_assert(make_ws_tab().ns_noarm == SENS_SLOTS_NOARM && make_ws_tab().ns == SENS_SLOTS, "ws slot count");
-
-template <bool ARM> struct WsCfg {
-    static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM;
-    static constexpr int ZERO = NS;                                   // an always-zero slot: target of the gather's structural zeros
-    static constexpr int NPAIR = (NS + 2) / 2;
-    // sub-tile (one stage of one pass) stride in doubles, == 4 (mod 8): the sixteen two-lane groups of a warp store
-    // spread over all banks (two wavefronts per STS.64, the minimum for 256 B)
-    static constexpr int PS = NPAIR * 4 + ((4 - (NPAIR * 4) % 8) + 8) % 8;
-    static constexpr int BUF = 16 * PS;                               // doubles per tile buffer: [4 stages][4 passes]
-    static constexpr int NB = (2 * WS_PRODUCERS * BUF * 8 + 512 <= (int)SF_SMEM_MAX) ? 2 : 1;    // buffers per producer
-    static constexpr int NBUF = NB * WS_PRODUCERS;
-    static constexpr size_t SMEM_TILES = sizeof(double) * BUF * NBUF;
-    static constexpr size_t SMEM_BARS = sizeof(unsigned long long) * 3 * NBUF;            // full, empty, meta
-    static constexpr size_t SMEM = SMEM_TILES + SMEM_BARS + sizeof(unsigned short) * 13 * 16;   // + gather offsets
-};
-
-struct WsSink {      // slot s of this lane's (unit, stage) at [stage][unit / 2][s / 2][unit % 2][s % 2]
-    double* base;
-    __device__ __forceinline__ void put(int s, double v) const { base[(s >> 1) * 4 + (s & 1)] = v; }
-    __device__ __forceinline__ void jx(int i, int j, double v) const { put(WS_TAB.slot[i][j], v); }
-    __device__ __forceinline__ void ju(int i, int j, double v) const { put(WS_TAB.slot[i][13 + j], v); }
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}"
-        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-template <bool ARM>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_sens_ws(const __grid_constant__ SensArgs a) {
-    using C = WsCfg<ARM>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* const tiles = reinterpret_cast<double*>(smem_raw);
-    unsigned long long* const full = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_TILES);
-    unsigned long long* const empty = full + C::NBUF;
-    long long* const meta = reinterpret_cast<long long*>(empty + C::NBUF);
-    unsigned short* const goff = reinterpret_cast<unsigned short*>(smem_raw + C::SMEM_TILES + C::SMEM_BARS);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long ngroups = (a.B + 31) / 32;
-    const double h6 = a.h / 6.0, hh = 0.5 * a.h;
-
-    if (threadIdx.x < C::NBUF) { mbar_init(full + threadIdx.x, 32); mbar_init(empty + threadIdx.x, 64); }
-    // byte offset (within a sub-tile) of entry (row i, tangent column c) of [Jx | Ju]; structural zeros -> the zero slot
-    if (threadIdx.x < 16) {
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            int sl = C::ZERO;
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-                if (c == (int)threadIdx.x && WS_TAB.slot[i][c] >= 0 && WS_TAB.slot[i][c] < C::NS) sl = WS_TAB.slot[i][c];
-            goff[i * 16 + threadIdx.x] = (unsigned short)(((sl >> 1) * 4 + (sl & 1)) * 8);
-        }
-    }
-    // the always-zero slot of every stage-1 sub-tile (never written afterwards)
-    for (int t = threadIdx.x; t < C::NBUF * 8; t += WS_THREADS)
-        tiles[(t >> 3) * C::BUF + ((t >> 1) & 3) * C::PS + (C::ZERO >> 1) * 4 + (t & 1) * 2 + (C::ZERO & 1)] = 0.0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    if (warp < WS_PRODUCERS) {
-        // =============================== producer ==========================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(KITE_WS_REGS_PRODUCER));
-        double* const Sw = a.Sw + ((long)blockIdx.x * WS_PRODUCERS + warp) * SF_SCRATCH_PER_WARP;
-        auto claim_group = [&]() -> long {
-            unsigned long long g = 0;
-            if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if ((long)g < ngroups) {                                    // pull the group's input lines into L2 (register free)
-                const long first = (long)g * 32;
-                const int row = lane >> 1;
-                const double* p = (row < 13 ? a.x + (long)row * a.ld : a.u + (long)(row - 13) * a.ld) + first + (lane & 1) * 16;
-                if (first + (lane & 1) * 16 < a.B) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-            }
-            return (long)g;
-        };
-        unsigned it = 0;                                                // tiles produced by this warp
-        long g = claim_group();
-        while (g < ngroups) {
-            const long g_next = claim_group();
-            // ---- step 1: lane = unit, primal RK4 step ----------------------------------------------------------
-            {
-                const long unit = g * 32 + lane;
-                const long ui = unit < a.B ? unit : a.B - 1;     // ragged tail: recompute the last unit, store nothing
-                double x[13], u[3], k[13], xt[13], acc[13];
-#pragma unroll
-                for (int c = 0; c < 13; ++c) { x[c] = __ldcs(a.x + (long)c * a.ld + ui); xt[c] = x[c]; }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { u[c] = __ldcs(a.u + (long)c * a.ld + ui); __stcg(Sw + (13 + c) * 32 + lane, u[c]); }
-                NoSink ns;
-#pragma unroll 1
-                for (int st = 0; st < 4; ++st) {
-#pragma unroll
-                    for (int c = 0; c < 13; ++c) __stcg(Sw + (st * 16 + c) * 32 + lane, xt[c]);
-                    model_eval<false, false>(a.K, a.K.A, xt, u, k, ns);
-                    const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-                    const double an = (st == 2) ? a.h : hh;
-#pragma unroll
-                    for (int c = 0; c < 13; ++c) {
-                        acc[c] = (st == 0) ? k[c] : fma(wgt, k[c], acc[c]);
-                        xt[c] = fma(an, k[c], x[c]);
-                    }
-                }
-                if (unit < a.B) {
-#pragma unroll
-                    for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, acc[c], x[c]));
-                }
-            }
-            __syncwarp();                               // the stage states of all 32 units are visible to the warp
-            // ---- step 2: lane = (unit, stage), four rounds of 8 units ------------------------------------------
-#pragma unroll 1
-            for (int r = 0; r < 4; ++r, ++it) {
-                const int b = warp * C::NB + (int)(it % C::NB);
-                const int u8 = lane & 7, s = lane >> 3;
-                double xt[13], u[3], k[13];
-#pragma unroll
-                for (int c = 0; c < 13; ++c) xt[c] = __ldcg(Sw + (s * 16 + c) * 32 + r * 8 + u8);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) u[c] = __ldcg(Sw + (13 + c) * 32 + r * 8 + u8);
-                mbar_wait(empty + b, ((it / C::NB) & 1) ^ 1);           // the consumers are done with this buffer
-                WsSink sink{tiles + (size_t)b * C::BUF + (s * 4 + (u8 >> 1)) * C::PS + (u8 & 1) * 2};
-                model_eval<false, true>(a.K, a.K.A, xt, u, k, sink);
-                if (lane == 0) meta[b] = g * 4 + r;
-                mbar_arrive(full + b);                                  // 32 arrivals complete the phase
-            }
-            g = g_next;
-        }
-        // termination: one more "tile" with a negative tag
-        {
-            const int b = warp * C::NB + (int)(it % C::NB);
-            mbar_wait(empty + b, ((it / C::NB) & 1) ^ 1);
-            if (lane == 0) meta[b] = -1;
-            mbar_arrive(full + b);
-        }
-    } else {
-        // =============================== consumer ==========================================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(KITE_WS_REGS_CONSUMER));
-        const int w = (warp - WS_PRODUCERS) % WS_PRODUCERS;             // the producer this warp serves (same scheduler)
-        const int q = (warp - WS_PRODUCERS) / WS_PRODUCERS;             // passes {2q, 2q+1} of each of its tiles
-        const int lu2 = lane >> 4, c = lane & 15;                       // unit of the pass, tangent column of this lane
-        double D[13], N[13], A[13];
-        const bool cu0 = c == 13, cu1 = c == 14, cu2 = c == 15;        // this lane carries a control column of the seed
-        unsigned it = 0;
-        while (true) {
-            const int b = w * C::NB + (int)(it % C::NB);
-            mbar_wait(full + b, (it / C::NB) & 1);
-            const long m = meta[b];
-            if (m < 0) break;
-            const double* const buf = tiles + (size_t)b * C::BUF;
-#pragma unroll 1
-            for (int pp = 0; pp < 2; ++pp) {
-                const int pass = 2 * q + pp;
-                const long unit = (m >> 2) * 32 + (m & 3) * 8 + pass * 2 + lu2;
-                // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of one Jacobian column (no FMAs)
-                {
-                    const char* T = reinterpret_cast<const char*>(buf + pass * C::PS + lu2 * 2);
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) N[i] = *reinterpret_cast<const double*>(T + goff[i * 16 + c]);
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) { A[i] = N[i]; D[i] = fma(hh, N[i], (i == c) ? 1.0 : 0.0); }
-                }
-                // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled)
-#pragma unroll 1
-                for (int st = 1; st < 4; ++st) {
-                    const double2* __restrict__ T = reinterpret_cast<const double2*>(buf + (st * 4 + pass) * C::PS + lu2 * 2);
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) N[i] = 0.0;
-#pragma unroll
-                    for (int kp = 0; kp < C::NPAIR; ++kp) {
-                        const int s0 = 2 * kp, s1 = 2 * kp + 1;
-                        const bool use0 = s0 < C::NS, use1 = s1 < C::NS;
-                        if (use0 || use1) {
-                            const double2 v = T[kp * 2];                 // broadcast LDS.128: two slots of this unit
-                            // state columns: DFMA with this lane's tangent; control columns (seed = constant unit
-                            // vector): the entry itself, on the lane that carries that column
-                            auto use = [&](int sl, double val) {
-#pragma unroll
-                                for (int n = 0; n < WS_TAB.nusers[sl]; ++n) {
-                                    const int i = WS_TAB.ui[sl][n], j = WS_TAB.uj[sl][n];
-                                    if (j < 13) N[i] = fma(val, D[j], N[i]);
-                                    else N[i] += ((j == 13) ? cu0 : (j == 14) ? cu1 : cu2) ? val : 0.0;
-                                }
-                            };
-                            if (use0) use(s0 < JAC_SLOTS ? s0 : 0, v.x);
-                            if (use1) use(s1 < JAC_SLOTS ? s1 : 0, v.y);
-                        }
-                    }
-                    const double wgt = (st == 3) ? 1.0 : 2.0;
-                    const double an = (st == 2) ? a.h : hh;
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) {
-                        A[i] = fma(wgt, N[i], A[i]);
-                        D[i] = fma(an, N[i], (i == c) ? 1.0 : 0.0);     // unused after the last stage
-                    }
-                }
-                if (unit < a.B) {
-                    // [Phi | Gamma] = E + h/6 A: row i of this lane's column
-                    double* const o = (c < 13) ? a.Phi + (long)c * a.ld + unit : a.Gamma + (long)(c - 13) * a.ld + unit;
-                    const long rs = (c < 13 ? 13 : 3) * a.ld;
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) __stcs(o + i * rs, fma(h6, A[i], (i == c) ? 1.0 : 0.0));
-                }
-            }
-            mbar_arrive(empty + b);                                     // 64 arrivals (two consumer warps) free the buffer
-            ++it;
-        }
     }
 }
 

@@ -1,5 +1,3 @@
-#include <cstdlib>
-
 #include "kite_launch.h"
 namespace kite {
 template <bool ARM, bool RIGID>
@@ -16,19 +14,6 @@ static void go_fused(const SensArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
     k_sens_fused<ARM, RIGID><<<grid, W * 32, SfCfg<ARM>::SMEM, s>>>(a);
 }
-template <bool ARM>
-static void go_ws(const SensArgs& a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_sens_ws<ARM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsCfg<ARM>::SMEM);
-        configured = true;
-    }
-    const long ngroups = (a.B + 31) / 32;
-    const long want = (ngroups + WS_PRODUCERS - 1) / WS_PRODUCERS;
-    const long sms = sens_fused_max_warps() / SF_WARPS;
-    const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
-    k_sens_ws<ARM><<<grid, WS_THREADS, WsCfg<ARM>::SMEM, s>>>(a);
-}
 long sens_fused_max_warps() {
     static long warps = 0;
     if (!warps) {
@@ -40,12 +25,8 @@ long sens_fused_max_warps() {
     return warps;
 }
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, cudaStream_t s) {
-    // kite models: the warp-specialised kernel; the rigid-body model (a 49-entry Jacobian) keeps the single-role one.
-    // KITE_SENS_SINGLE_ROLE=1 selects the single-role kernel for every model (developer comparison switch).
-    static const bool single_role = getenv("KITE_SENS_SINGLE_ROLE") && getenv("KITE_SENS_SINGLE_ROLE")[0] == '1';
     if (rigid) go_fused<false, true>(a, s);
-    else if (single_role) { if (arm) go_fused<true, false>(a, s); else go_fused<false, false>(a, s); }
-    else if (arm) go_ws<true>(a, s);
-    else go_ws<false>(a, s);
+    else if (arm) go_fused<true, false>(a, s);
+    else go_fused<false, false>(a, s);
 }
 }  // namespace kite
