@@ -328,9 +328,16 @@ static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, co
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemsetAsync(ctx->counters.ptr, 0, 8, ctx->stream));
-    SensArgs a{ctx->K, B, ld, h, x, u, xn, Phi, Gamma, (double*)work, (unsigned long long*)ctx->counters.ptr};
+    SensArgs a{};
+    a.K = ctx->K; a.B = B; a.ld = ld; a.h = h; a.x = x; a.u = u; a.xn = xn; a.Phi = Phi; a.Gamma = Gamma;
+    a.Sw = (double*)work; a.next_group = (unsigned long long*)ctx->counters.ptr;
     (void)ldw;
-    launch_sens_fused(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    // [Phi | Gamma] leave through TMA tensor stores when the output layout allows it (16-byte aligned base and pitch:
+    // an even ld); KITE_SENS_DIRECT_STORES=1 forces the direct-store kernel (developer comparison switch)
+    static const bool direct = getenv("KITE_SENS_DIRECT_STORES") && getenv("KITE_SENS_DIRECT_STORES")[0] == '1';
+    const bool tma_out = !rigid && !direct && sens_make_tensor_map(&a.tmPhi, Phi, B, ld, 169) &&
+                         sens_make_tensor_map(&a.tmGam, Gamma, B, ld, 39);
+    launch_sens_fused(a, rigid, ctx->K.has_arm != 0, tma_out, ctx->stream);
     LAUNCH_CHECK("k_sens_fused");
     return KITE_OK;
 }

@@ -8,6 +8,7 @@
 // the constant bank as DFMA operands and cost no registers.
 // =====================================================================================
 #pragma once
+#include <cuda.h>
 #include <cuda_pipeline.h>
 
 #include "kite_model.cuh"
@@ -247,6 +248,8 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 //   No TMA, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
 // ================================================================================================
 struct SensArgs {
+    alignas(64) CUtensorMap tmPhi;    // [169][B] rows of ld doubles, box [169][4 units]  (only read by the TMA-output kernels)
+    alignas(64) CUtensorMap tmGam;    // [39][B], box [39][4 units]
     KiteConsts K;
     long B, ld;
     double h;
@@ -306,12 +309,26 @@ template <bool ARM> struct SfCfg {
     // tile stride: + one zero row (target of the gather's structural zeros), and == 4 (mod 16) doubles so that the 8
     // four-lane groups (stage, pass) of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
     static constexpr int TILE_S = TILE + 4 + ((4 - (TILE + 4) % 16) + 16) % 16;
-    static constexpr size_t SMEM_PER_WARP = sizeof(double) * 8 * TILE_S;          // [4 stages][2 passes] tiles
+    // a warp's tiles are laid out [pass][stage]; the pass stride is == 8 (mod 16) doubles so that the four (stage, pass)
+    // groups of a half-warp store still land in distinct bank octets
+    static constexpr int PASS_S = 4 * TILE_S + 8;
+    static constexpr size_t SMEM_PER_WARP = sizeof(double) * 2 * PASS_S;
     static constexpr int FIT = (int)((SF_SMEM_MAX - 2048) / SMEM_PER_WARP);
     static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
     static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
     static constexpr size_t SMEM = SMEM_TILES + sizeof(unsigned) * 13 * 32;       // + gather table
+    // TMA output: the [169][4] and [39][4] boxes of a pass are staged in the pass's own stage-3 / stage-4 tiles (dead
+    // once the pass has consumed them), at 128-byte aligned offsets (bytes from the warp's base)
+    __host__ __device__ static constexpr size_t up128(size_t v) { return (v + 127) / 128 * 128; }
+    __host__ __device__ static constexpr size_t box_phi(int p) { return up128(sizeof(double) * (p * PASS_S + 2 * TILE_S)); }
+    __host__ __device__ static constexpr size_t box_gam(int p) { return up128(box_phi(p) + sizeof(double) * 169 * 4); }
 };
+static_assert(SfCfg<false>::SMEM_PER_WARP % 128 == 0 && SfCfg<true>::SMEM_PER_WARP % 128 == 0, "TMA staging alignment");
+static_assert(SfCfg<false>::box_gam(0) + 39 * 32 <= sizeof(double) * (SfCfg<false>::PASS_S - 8) &&
+              SfCfg<false>::box_gam(1) + 39 * 32 <= sizeof(double) * (2 * SfCfg<false>::PASS_S - 8) &&
+              SfCfg<true>::box_gam(0) + 39 * 32 <= sizeof(double) * (SfCfg<true>::PASS_S - 8) &&
+              SfCfg<true>::box_gam(1) + 39 * 32 <= sizeof(double) * (2 * SfCfg<true>::PASS_S - 8), "staging boxes fit the dead tiles");
+static_assert(SfCfg<false>::PASS_S % 16 == 8 && SfCfg<true>::PASS_S % 16 == 8, "pass stride");
 static_assert(SfCfg<false>::TILE_S % 16 == 4 && SfCfg<true>::TILE_S % 16 == 4, "tile stride");
 static_assert(SfCfg<false>::TILE_S >= SfCfg<false>::TILE + 4 && SfCfg<true>::TILE_S >= SfCfg<true>::TILE + 4, "zero row");
 
@@ -321,19 +338,19 @@ struct StageSink {      // the warp's tile: compact slots of this lane's (unit, 
     __device__ __forceinline__ void ju(int i, int j, double v) const { base[SENS_TAB.ju[i][j] * 4] = v; }
 };
 
-template <bool ARM, bool RIGID>
+template <bool ARM, bool RIGID, bool TMA_OUT>
 __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const __grid_constant__ SensArgs a) {
     using C = SfCfg<ARM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* const tile = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 8 * C::TILE_S;
+    double* const tile = reinterpret_cast<double*>(smem_raw + (size_t)warp * C::SMEM_PER_WARP);
     double* const Sw = a.Sw + ((long)blockIdx.x * C::WARPS + warp) * SF_SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
-    const int c0 = 2 * l, c1 = 2 * l + 1;          // tangent columns of this lane in phase B
+    const int c0 = l, c1 = l + 8;                  // tangent columns of this lane in phase B
 
     // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
-    if (lane < 8) tile[(lane >> 2) * C::TILE_S + C::TILE + (lane & 3)] = 0.0;
+    if (lane < 8) tile[(lane >> 2) * C::PASS_S + C::TILE + (lane & 3)] = 0.0;
     // gather table: byte offsets (within a tile, lane's unit included) of the entries of Jacobian columns c0 (low half)
     // and c1 (high half) of this lane, one word per row; structural zeros point at the zero row.  [13][32 lanes].
     unsigned* const goff = reinterpret_cast<unsigned*>(smem_raw + C::SMEM_TILES) + lane;
@@ -414,7 +431,11 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 for (int c = 0; c < 13; ++c) xt[c] = __ldcg(Sw + (s * 16 + c) * 32 + r * 8 + u8);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) u[c] = __ldcg(Sw + (13 + c) * 32 + r * 8 + u8);
-                StageSink sink{tile + (s * 2 + (u8 >> 2)) * C::TILE_S + (u8 & 3)};
+                StageSink sink{tile + (u8 >> 2) * C::PASS_S + s * C::TILE_S + (u8 & 3)};
+                if (TMA_OUT) {                          // the previous round's output boxes have left the tiles
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
                 model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
             }
 #endif
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 const long unit = g * 32 + r * 8 + p * 4 + lu;
                 // ---- stage 1: D = E, so S_1 = [Jx | Ju] E is a gather of two Jacobian columns (no FMAs)
                 {
-                    const char* const T = reinterpret_cast<const char*>(tile + p * C::TILE_S);
+                    const char* const T = reinterpret_cast<const char*>(tile + p * C::PASS_S);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
                         const unsigned o = goff[i * 32];
@@ -446,7 +467,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled: instruction-cache footprint)
 #pragma unroll 1
                 for (int st = 1; st < 4; ++st) {
-                    const double* __restrict__ T = tile + (st * 2 + p) * C::TILE_S + lu;
+                    const double* __restrict__ T = tile + p * C::PASS_S + st * C::TILE_S + lu;
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
                     // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
@@ -477,7 +498,35 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                         }
                     }
                 }
-                if (unit < a.B) {
+                if (TMA_OUT) {
+                    // [Phi | Gamma] = E + h/6 A staged as the [169][4] / [39][4] boxes of this pass (shared-memory stores with
+                    // immediate offsets) and written by two TMA tensor stores: the LSU sees 26 four-wavefront shared stores
+                    // instead of 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by
+                    // the tensor map
+                    unsigned char* const wb = smem_raw + (size_t)warp * C::SMEM_PER_WARP;
+                    double* const bphi = reinterpret_cast<double*>(wb + (p ? C::box_phi(1) : C::box_phi(0)));
+                    double* const bgam = reinterpret_cast<double*>(wb + (p ? C::box_gam(1) : C::box_gam(0)));
+                    double* const o0 = bphi + c0 * 4 + lu;
+                    double* const o1 = (c1 < 13) ? bphi + c1 * 4 + lu : bgam + (c1 - 13) * 4 + lu;
+                    const int rs1 = (c1 < 13) ? 52 : 12;
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        o0[i * 52] = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+                        o1[i * rs1] = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int ux = (int)(g * 32 + r * 8 + p * 4);
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     :: "l"(reinterpret_cast<unsigned long long>(&a.tmPhi)), "r"(ux), "r"(0),
+                                        "r"((unsigned)__cvta_generic_to_shared(bphi)) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     :: "l"(reinterpret_cast<unsigned long long>(&a.tmGam)), "r"(ux), "r"(0),
+                                        "r"((unsigned)__cvta_generic_to_shared(bgam)) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (unit < a.B) {
                     // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
                     double* const o0 = (c0 < 13) ? a.Phi + (long)c0 * a.ld + unit : a.Gamma + (long)(c0 - 13) * a.ld + unit;
                     double* const o1 = (c1 < 13) ? a.Phi + (long)c1 * a.ld + unit : a.Gamma + (long)(c1 - 13) * a.ld + unit;
@@ -494,6 +543,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
         }
         g = g_next;
     }
+    if (TMA_OUT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ================================================================================================

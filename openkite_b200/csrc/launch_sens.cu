@@ -1,10 +1,12 @@
+#include <cstdint>
+
 #include "kite_launch.h"
 namespace kite {
-template <bool ARM, bool RIGID>
+template <bool ARM, bool RIGID, bool TMA_OUT>
 static void go_fused(const SensArgs& a, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_sens_fused<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
+        cudaFuncSetAttribute(k_sens_fused<ARM, RIGID, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
         configured = true;
     }
     const long ngroups = (a.B + 31) / 32;
@@ -12,7 +14,7 @@ static void go_fused(const SensArgs& a, cudaStream_t s) {
     const long want = (ngroups + W - 1) / W;
     const long sms = sens_fused_max_warps() / SF_WARPS;
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
-    k_sens_fused<ARM, RIGID><<<grid, W * 32, SfCfg<ARM>::SMEM, s>>>(a);
+    k_sens_fused<ARM, RIGID, TMA_OUT><<<grid, W * 32, SfCfg<ARM>::SMEM, s>>>(a);
 }
 long sens_fused_max_warps() {
     static long warps = 0;
@@ -24,9 +26,39 @@ long sens_fused_max_warps() {
     }
     return warps;
 }
-void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, cudaStream_t s) {
-    if (rigid) go_fused<false, true>(a, s);
-    else if (arm) go_fused<true, false>(a, s);
-    else go_fused<false, false>(a, s);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn encode_tiled() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][4 units].  False when the layout does not
+// meet the TMA constraints (16-byte aligned base and pitch; an even B, because the TMA clips out-of-range columns in
+// 16-byte units and an odd B would spill one double into the padding): the caller then uses the direct-store kernel.
+bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows) {
+    encode_tiled_fn enc = encode_tiled();
+    if (!enc || !base || B <= 0 || (B & 1) || B >= (1L << 31) || ((uintptr_t)base & 15) || ((ld * 8) & 15) || ld * 8 >= (1L << 40)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {4, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s) {
+    if (rigid) go_fused<false, true, false>(a, s);
+    else if (arm) { if (tma_out) go_fused<true, false, true>(a, s); else go_fused<true, false, false>(a, s); }
+    else { if (tma_out) go_fused<false, false, true>(a, s); else go_fused<false, false, false>(a, s); }
 }
 }  // namespace kite

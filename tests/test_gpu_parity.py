@@ -281,6 +281,35 @@ def test_sens_scratch_stays_inside_work_bytes(eng, oracle):
             assert_close(aos(Phi, 13, 13), rPhi, RTOL, what="Phi B=%d" % B)
 
 
+def test_sens_tma_output_matches_direct_stores(eng, oracle):
+    """[Phi | Gamma] leave through TMA tensor stores when base and pitch are 16-byte aligned and B is even, through direct
+    stores otherwise: both paths must give bitwise the same result, match the oracle, clip the ragged tail and leave the
+    padding columns alone."""
+    import ctypes as C
+    h = 0.02
+    for B in (1001, 4, 1002, 37, 2050):
+        x = oracle.synth_x0(5, B); u = oracle.synth_controls(5, B, 1)[:, 0, :]
+        rxn, rPhi, rGam = oracle.rk4_sens(x, u, h)
+        res = []
+        for ld in (B + (B & 1) + 6, B + 1 - (B & 1) + 6):          # even pitch (TMA), odd pitch (direct stores)
+            xd = torch.zeros(13, ld, dtype=torch.float64, device="cuda"); xd[:, :B] = soa(x)
+            ud = torch.zeros(3, ld, dtype=torch.float64, device="cuda"); ud[:, :B] = soa(u)
+            xn = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda")
+            Phi = torch.full((169, ld), -7.0, dtype=torch.float64, device="cuda")
+            Gam = torch.full((39, ld), -7.0, dtype=torch.float64, device="cuda")
+            w = eng.workspace(eng.L.kite_rk4_sens_work_bytes(B))
+            p = lambda t: C.c_void_p(t.data_ptr())
+            eng._use_torch_stream()
+            eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, B, ld, h, p(xd), p(ud), p(xn), p(Phi), p(Gam), p(w)))
+            torch.cuda.synchronize()
+            assert float((Phi[:, B:] + 7.0).abs().max()) == 0.0 and float((Gam[:, B:] + 7.0).abs().max()) == 0.0, "padding written"
+            assert_close(aos(Phi[:, :B], 13, 13), rPhi, RTOL, what="Phi B=%d ld=%d" % (B, ld))
+            assert_close(aos(Gam[:, :B], 13, 3), rGam, RTOL, what="Gamma B=%d ld=%d" % (B, ld))
+            assert_close(aos(xn[:, :B]), rxn, RTOL, what="xn B=%d ld=%d" % (B, ld))
+            res.append((Phi[:, :B].clone(), Gam[:, :B].clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), "TMA and direct-store outputs differ"
+
+
 def test_sens_linearity_property(eng, oracle):
     """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
     B, h = 2048, 0.02
