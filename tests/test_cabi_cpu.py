@@ -66,12 +66,13 @@ def test_no_cpu_fallback(lib, yaml_path):
 
 
 def test_work_size_queries(lib):
-    # sensitivity kernel: one private [4 stages][132 slots][32 units] region per resident warp of the persistent grid
-    # (6 warps per CTA, one CTA per 6 groups of 32 units, capped at the SM count; 256 SMs assumed without a device)
-    per_warp = 8 * 4 * 132 * 32
-    assert lib.kite_rk4_sens_work_bytes(10) == 6 * per_warp
-    assert lib.kite_rk4_sens_work_bytes(32 * 6 + 1) == 12 * per_warp
+    # sensitivity kernel: one private [4 stages][x(13) | u(3)][32 units] line of stage states per resident warp of the
+    # persistent grid (at most 8 warps per CTA, capped at the SM count; 256 SMs assumed without a device); the stage
+    # Jacobians themselves stay in shared memory
+    per_warp = 8 * 4 * 16 * 32
+    assert lib.kite_rk4_sens_work_bytes(10) == (1 + 8) * per_warp            # groups + one CTA of slack
+    assert lib.kite_rk4_sens_work_bytes(32 * 6 + 1) == (7 + 8) * per_warp
     big = lib.kite_rk4_sens_work_bytes(1 << 24)
-    assert big % (6 * per_warp) == 0 and 8 <= big // per_warp <= 256 * 8
+    assert big % per_warp == 0 and 8 <= big // per_warp <= 256 * 8
     assert lib.kite_ekf_work_bytes(10) == 0          # EKF predict keeps the Jacobian in shared memory
     assert lib.kite_rk4_sens_work_bytes(0) == 0
