@@ -31,6 +31,7 @@ __host__ __device__ constexpr bool ju_nz(int i, int j) {
            (i == 1 && j == 2) || (i == 3 && j == 2) || (i == 5 && j == 2);
 }
 constexpr int JAC_SLOTS = JX_SLOTS + 7;   // 132
+constexpr int JX_SLOTS_NOARM_ONLY = 104;  // the state-Jacobian entries of a zero-arm model are the first 104 slots
 struct SlotTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
 constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7: the slots a zero-arm model touches are the first 111
 constexpr SlotTab make_slot_tab() {
@@ -689,6 +690,155 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
         }
         __syncwarp();                                   // phase B is done with the Jacobian tile before the next group
     }
+}
+
+// ================================================================================================
+// EKF predict, covariance through TMA boxes (the product path when the covariance layout is TMA-addressable: 16-byte
+// aligned base and pitch, even B).  Same arithmetic and warp structure as k_ekf_predict; what changes is how P moves.
+// The [169][4 filters] box of a pass arrives in the warp's shared memory by ONE TMA tensor load (issued half a pass
+// ahead, completion on an mbarrier), rows of P are read from it, Q = P A^T is written back IN PLACE (a lane only ever
+// overwrites the entries it read), the columns of Q are read from the same box (the box is the transpose buffer), the
+// columns of Pn = A Q + W are written in place again and the box leaves by ONE TMA tensor store.  The LSU sees 4-wavefront
+// shared accesses with immediate offsets instead of 52 eight-sector global accesses with 64-bit address arithmetic per
+// pass (profiles/r1zb_ekf_before_ncu_summary.txt: LSU data pipe 63 % busy, 39 % of it global sectors).
+// ================================================================================================
+struct EkfTmaArgs {
+    alignas(64) CUtensorMap tmP;      // [169][B] rows of ld doubles, box [169][4 filters]
+    alignas(64) CUtensorMap tmPn;
+    EkfArgs e;
+};
+template <bool ARM> struct EtCfg {
+    static constexpr int WARPS = ARM ? 5 : 6;
+    static constexpr int NS = ARM ? JAC_SLOTS : JX_SLOTS_NOARM_ONLY;  // state-Jacobian slots only (the EKF needs no Ju)
+    static constexpr int PS = NS * 4 + ((NS * 4) % 16 == 12 ? 8 : ((NS * 4) % 16 == 0 ? 4 : (20 - (NS * 4) % 16) % 16));
+    static constexpr size_t BOX = 5504;                               // 169 x 4 x 8 B = 5408, rounded up to 128 B
+    static constexpr unsigned BOX_BYTES = 169 * 4 * 8;
+    static constexpr size_t PER_WARP = 2 * BOX + sizeof(double) * 8 * PS;      // two boxes + the Jacobian tile
+    static constexpr size_t SMEM_WARPS = PER_WARP * WARPS;
+    static constexpr size_t SMEM = SMEM_WARPS + sizeof(double) * 176 + sizeof(unsigned long long) * 2 * WARPS;   // + W, mbarriers
+};
+static_assert(EtCfg<false>::PS % 16 == 4 && EtCfg<true>::PS % 16 == 4, "bank-conflict-free pass stride");
+static_assert(EtCfg<false>::PER_WARP % 128 == 0 && EtCfg<true>::PER_WARP % 128 == 0, "TMA box alignment");
+static_assert(EtCfg<false>::SMEM <= SF_SMEM_MAX && EtCfg<true>::SMEM <= SF_SMEM_MAX, "shared memory");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <bool ARM, bool RIGID>
+__global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(const __grid_constant__ EkfTmaArgs ta) {
+    using C = EtCfg<ARM>;
+    const EkfArgs& a = ta.e;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const wb = smem_raw + (size_t)warp * C::PER_WARP;
+    double* const Jt = reinterpret_cast<double*>(wb + 2 * C::BOX);
+    const double* const Ws = reinterpret_cast<const double*>(smem_raw + C::SMEM_WARPS);      // W (13 x 13 row-major), one copy per CTA
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_WARPS + sizeof(double) * 176) + warp * 2;
+    const long ngroups = (a.B + 31) / 32;
+    const int lu = lane >> 3, l = lane & 7;
+    const int r0 = l, r1 = l + 8;                  // rows of P (first product) = columns of Pn (second product)
+    const bool v1 = r1 < 13;
+
+    for (int t = threadIdx.x; t < 169; t += blockDim.x) reinterpret_cast<double*>(smem_raw + C::SMEM_WARPS)[t] = __ldg(a.W + t);
+    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + lane)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // box of pass `t` of the warp's pass sequence -> buffer t & 1, one TMA tensor load issued by lane 0
+    auto issue_load = [&](unsigned t, long first_unit) {
+        if (lane == 0) {
+            const unsigned bar = smem_u32(bars + (t & 1));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::BOX_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         :: "r"(smem_u32(wb + (t & 1) * C::BOX)), "l"(reinterpret_cast<unsigned long long>(&ta.tmP)),
+                            "r"((int)first_unit), "r"(0), "r"(bar) : "memory");
+        }
+    };
+    auto claim_group = [&]() -> long {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
+        return (long)__shfl_sync(0xffffffffu, g, 0);
+    };
+    unsigned t = 0;                                 // passes done by this warp (buffer and mbarrier phase bookkeeping)
+    for (long g = claim_group(); g < ngroups; g = claim_group()) {
+        // the first pass's box lands behind phase A (both buffers are free here: the stores of the previous group have
+        // been waited for in its last pass ... except the very last one)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        issue_load(t, g * 32);
+        // ---------------- phase A: lane = filter ------------------------------------------------------------
+        {
+            const long unit = g * 32 + lane;
+            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
+            double x[13], u[3], f[13];
+#pragma unroll
+            for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
+            {
+                SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
+                model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
+            }
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
+            if (unit < a.B) {
+#pragma unroll
+                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B: 8 lanes = filter, 4 filters per pass -------------------------------------
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p, ++t) {
+            const double* __restrict__ T = Jt + p * C::PS + lu;
+            double* const box = reinterpret_cast<double*>(wb + (t & 1) * C::BOX) + lu;
+            double p0[13], p1[13], n0[13], n1[13];
+            mbar_wait(bars + (t & 1), (t >> 1) & 1);
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {              // rows r0, r1 of P
+                p0[k] = box[(r0 * 13 + k) * 4];
+                p1[k] = v1 ? box[(r1 * 13 + k) * 4] : 0.0;
+            }
+            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {              // rows r0, r1 of Q = P A^T, in place
+                box[(r0 * 13 + k) * 4] = fma(a.dt, n0[k], p0[k]);
+                if (v1) box[(r1 * 13 + k) * 4] = fma(a.dt, n1[k], p1[k]);
+            }
+            __syncwarp();
+            // half a pass after the previous pass's store was issued: its buffer has been read, the next box may land in it
+            if (p < 7) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_load(t + 1, g * 32 + (p + 1) * 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {              // columns r0, r1 of Q
+                p0[k] = box[(k * 13 + r0) * 4];
+                p1[k] = v1 ? box[(k * 13 + r1) * 4] : 0.0;
+            }
+            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+#pragma unroll
+            for (int i = 0; i < 13; ++i) {              // columns r0, r1 of Pn = A Q + W, in place
+                box[(i * 13 + r0) * 4] = fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0];
+                if (v1) box[(i * 13 + r1) * 4] = fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {                            // filters >= B are clipped by the tensor map
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             :: "l"(reinterpret_cast<unsigned long long>(&ta.tmPn)), "r"((int)(g * 32 + p * 4)), "r"(0),
+                                "r"(smem_u32(wb + (t & 1) * C::BOX)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        __syncwarp();                                   // phase B is done with the Jacobian tile before the next group
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // EKF measurement update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125), thread per filter, out of place for P:
