@@ -31,7 +31,6 @@ __host__ __device__ constexpr bool ju_nz(int i, int j) {
            (i == 1 && j == 2) || (i == 3 && j == 2) || (i == 5 && j == 2);
 }
 constexpr int JAC_SLOTS = JX_SLOTS + 7;   // 132
-constexpr int JX_SLOTS_NOARM_ONLY = 104;  // the state-Jacobian entries of a zero-arm model are the first 104 slots
 struct SlotTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
 constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7: the slots a zero-arm model touches are the first 111
 constexpr SlotTab make_slot_tab() {
@@ -249,8 +248,8 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 //   No TMA, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
 // ================================================================================================
 struct SensArgs {
-    alignas(64) CUtensorMap tmPhi;    // [169][B] rows of ld doubles, box [169][4 units]  (only read by the TMA-output kernels)
-    alignas(64) CUtensorMap tmGam;    // [39][B], box [39][4 units]
+    alignas(64) CUtensorMap tmPhi;    // [169][B] rows of ld doubles, box [169][8 units]  (only read by the TMA-output kernels)
+    alignas(64) CUtensorMap tmGam;    // [39][B], box [39][8 units]
     KiteConsts K;
     long B, ld;
     double h;
@@ -318,17 +317,16 @@ template <bool ARM> struct SfCfg {
     static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
     static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
     static constexpr size_t SMEM = SMEM_TILES + sizeof(unsigned) * 13 * 32;       // + gather table
-    // TMA output: the [169][4] and [39][4] boxes of a pass are staged in the pass's own stage-3 / stage-4 tiles (dead
-    // once the pass has consumed them), at 128-byte aligned offsets (bytes from the warp's base)
+    // TMA output: the [169][8] and [39][8] boxes of a ROUND (both passes) are staged in pass 0's tiles, all four dead once
+    // pass 0 has consumed them (bytes from the warp's base, 128-byte aligned).  The [169] box runs over the zero row of
+    // pass 0's stage-1 tile, which is restored after the TMA has read the box.
     __host__ __device__ static constexpr size_t up128(size_t v) { return (v + 127) / 128 * 128; }
-    __host__ __device__ static constexpr size_t box_phi(int p) { return up128(sizeof(double) * (p * PASS_S + 2 * TILE_S)); }
-    __host__ __device__ static constexpr size_t box_gam(int p) { return up128(box_phi(p) + sizeof(double) * 169 * 4); }
+    static constexpr size_t BOX_PHI = 0;
+    static constexpr size_t BOX_GAM = (sizeof(double) * 169 * 8 + 127) / 128 * 128;
 };
 static_assert(SfCfg<false>::SMEM_PER_WARP % 128 == 0 && SfCfg<true>::SMEM_PER_WARP % 128 == 0, "TMA staging alignment");
-static_assert(SfCfg<false>::box_gam(0) + 39 * 32 <= sizeof(double) * (SfCfg<false>::PASS_S - 8) &&
-              SfCfg<false>::box_gam(1) + 39 * 32 <= sizeof(double) * (2 * SfCfg<false>::PASS_S - 8) &&
-              SfCfg<true>::box_gam(0) + 39 * 32 <= sizeof(double) * (SfCfg<true>::PASS_S - 8) &&
-              SfCfg<true>::box_gam(1) + 39 * 32 <= sizeof(double) * (2 * SfCfg<true>::PASS_S - 8), "staging boxes fit the dead tiles");
+static_assert(SfCfg<false>::BOX_GAM + 39 * 64 <= sizeof(double) * (SfCfg<false>::PASS_S - 8) &&
+              SfCfg<true>::BOX_GAM + 39 * 64 <= sizeof(double) * (SfCfg<true>::PASS_S - 8), "staging boxes fit pass 0's tiles");
 static_assert(SfCfg<false>::PASS_S % 16 == 8 && SfCfg<true>::PASS_S % 16 == 8, "pass stride");
 static_assert(SfCfg<false>::TILE_S % 16 == 4 && SfCfg<true>::TILE_S % 16 == 4, "tile stride");
 static_assert(SfCfg<false>::TILE_S >= SfCfg<false>::TILE + 4 && SfCfg<true>::TILE_S >= SfCfg<true>::TILE + 4, "zero row");
@@ -347,7 +345,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     double* const tile = reinterpret_cast<double*>(smem_raw + (size_t)warp * C::SMEM_PER_WARP);
     double* const Sw = a.Sw + ((long)blockIdx.x * C::WARPS + warp) * SF_SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
-    const int lu = lane >> 3, l = lane & 7;
+    // phase B: lane = (column pair l, unit lu of the pass) with the unit in the LOW lane bits, so that a half-warp store
+    // into the output box covers 4 rows x 4 units (2-way bank conflicts at the box's 64-byte row pitch instead of 4-way)
+    const int lu = lane & 3, l = lane >> 2;
     const int c0 = l, c1 = l + 8;                  // tangent columns of this lane in phase B
 
     // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 if (TMA_OUT) {                          // the previous round's output boxes have left the tiles
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
+                    if (lane < 4) tile[C::TILE + lane] = 0.0;          // pass 0's zero row lay under the [169][8] box
                 }
                 model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
             }
@@ -500,32 +501,36 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                     }
                 }
                 if (TMA_OUT) {
-                    // [Phi | Gamma] = E + h/6 A staged as the [169][4] / [39][4] boxes of this pass (shared-memory stores with
-                    // immediate offsets) and written by two TMA tensor stores: the LSU sees 26 four-wavefront shared stores
-                    // instead of 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by
-                    // the tensor map
+                    // [Phi | Gamma] = E + h/6 A staged in the [169][8] / [39][8] boxes of the round (units 4 p .. 4 p + 3 of
+                    // every row; shared-memory stores with immediate offsets) and, after the second pass, written by two
+                    // TMA tensor stores of 64-byte rows: the LSU sees 26 four-wavefront shared stores per pass instead
+                    // of 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by the
+                    // tensor map
                     unsigned char* const wb = smem_raw + (size_t)warp * C::SMEM_PER_WARP;
-                    double* const bphi = reinterpret_cast<double*>(wb + (p ? C::box_phi(1) : C::box_phi(0)));
-                    double* const bgam = reinterpret_cast<double*>(wb + (p ? C::box_gam(1) : C::box_gam(0)));
-                    double* const o0 = bphi + c0 * 4 + lu;
-                    double* const o1 = (c1 < 13) ? bphi + c1 * 4 + lu : bgam + (c1 - 13) * 4 + lu;
-                    const int rs1 = (c1 < 13) ? 52 : 12;
+                    double* const bphi = reinterpret_cast<double*>(wb + C::BOX_PHI);
+                    double* const bgam = reinterpret_cast<double*>(wb + C::BOX_GAM);
+                    double* const o0 = bphi + c0 * 8 + p * 4 + lu;
+                    double* const o1 = ((c1 < 13) ? bphi + c1 * 8 : bgam + (c1 - 13) * 8) + p * 4 + lu;
+                    const int rs1 = (c1 < 13) ? 104 : 24;
+                    if (p == 0) __syncwarp();           // every lane is done with pass 0's tiles (the box lies over them)
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
-                        o0[i * 52] = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+                        o0[i * 104] = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
                         o1[i * rs1] = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int ux = (int)(g * 32 + r * 8 + p * 4);
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                     :: "l"(reinterpret_cast<unsigned long long>(&a.tmPhi)), "r"(ux), "r"(0),
-                                        "r"((unsigned)__cvta_generic_to_shared(bphi)) : "memory");
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                     :: "l"(reinterpret_cast<unsigned long long>(&a.tmGam)), "r"(ux), "r"(0),
-                                        "r"((unsigned)__cvta_generic_to_shared(bgam)) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (p == 1) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int ux = (int)(g * 32 + r * 8);
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmPhi)), "r"(ux), "r"(0),
+                                            "r"((unsigned)__cvta_generic_to_shared(bphi)) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmGam)), "r"(ux), "r"(0),
+                                            "r"((unsigned)__cvta_generic_to_shared(bgam)) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                     }
                 } else if (unit < a.B) {
                     // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
@@ -690,155 +695,6 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
         }
         __syncwarp();                                   // phase B is done with the Jacobian tile before the next group
     }
-}
-
-// ================================================================================================
-// EKF predict, covariance through TMA boxes (the product path when the covariance layout is TMA-addressable: 16-byte
-// aligned base and pitch, even B).  Same arithmetic and warp structure as k_ekf_predict; what changes is how P moves.
-// The [169][4 filters] box of a pass arrives in the warp's shared memory by ONE TMA tensor load (issued half a pass
-// ahead, completion on an mbarrier), rows of P are read from it, Q = P A^T is written back IN PLACE (a lane only ever
-// overwrites the entries it read), the columns of Q are read from the same box (the box is the transpose buffer), the
-// columns of Pn = A Q + W are written in place again and the box leaves by ONE TMA tensor store.  The LSU sees 4-wavefront
-// shared accesses with immediate offsets instead of 52 eight-sector global accesses with 64-bit address arithmetic per
-// pass (profiles/r1zb_ekf_before_ncu_summary.txt: LSU data pipe 63 % busy, 39 % of it global sectors).
-// ================================================================================================
-struct EkfTmaArgs {
-    alignas(64) CUtensorMap tmP;      // [169][B] rows of ld doubles, box [169][4 filters]
-    alignas(64) CUtensorMap tmPn;
-    EkfArgs e;
-};
-template <bool ARM> struct EtCfg {
-    static constexpr int WARPS = ARM ? 5 : 6;
-    static constexpr int NS = ARM ? JAC_SLOTS : JX_SLOTS_NOARM_ONLY;  // state-Jacobian slots only (the EKF needs no Ju)
-    static constexpr int PS = NS * 4 + ((NS * 4) % 16 == 12 ? 8 : ((NS * 4) % 16 == 0 ? 4 : (20 - (NS * 4) % 16) % 16));
-    static constexpr size_t BOX = 5504;                               // 169 x 4 x 8 B = 5408, rounded up to 128 B
-    static constexpr unsigned BOX_BYTES = 169 * 4 * 8;
-    static constexpr size_t PER_WARP = 2 * BOX + sizeof(double) * 8 * PS;      // two boxes + the Jacobian tile
-    static constexpr size_t SMEM_WARPS = PER_WARP * WARPS;
-    static constexpr size_t SMEM = SMEM_WARPS + sizeof(double) * 176 + sizeof(unsigned long long) * 2 * WARPS;   // + W, mbarriers
-};
-static_assert(EtCfg<false>::PS % 16 == 4 && EtCfg<true>::PS % 16 == 4, "bank-conflict-free pass stride");
-static_assert(EtCfg<false>::PER_WARP % 128 == 0 && EtCfg<true>::PER_WARP % 128 == 0, "TMA box alignment");
-static_assert(EtCfg<false>::SMEM <= SF_SMEM_MAX && EtCfg<true>::SMEM <= SF_SMEM_MAX, "shared memory");
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}"
-        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-template <bool ARM, bool RIGID>
-__global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(const __grid_constant__ EkfTmaArgs ta) {
-    using C = EtCfg<ARM>;
-    const EkfArgs& a = ta.e;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* const wb = smem_raw + (size_t)warp * C::PER_WARP;
-    double* const Jt = reinterpret_cast<double*>(wb + 2 * C::BOX);
-    const double* const Ws = reinterpret_cast<const double*>(smem_raw + C::SMEM_WARPS);      // W (13 x 13 row-major), one copy per CTA
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::SMEM_WARPS + sizeof(double) * 176) + warp * 2;
-    const long ngroups = (a.B + 31) / 32;
-    const int lu = lane >> 3, l = lane & 7;
-    const int r0 = l, r1 = l + 8;                  // rows of P (first product) = columns of Pn (second product)
-    const bool v1 = r1 < 13;
-
-    for (int t = threadIdx.x; t < 169; t += blockDim.x) reinterpret_cast<double*>(smem_raw + C::SMEM_WARPS)[t] = __ldg(a.W + t);
-    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + lane)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    // box of pass `t` of the warp's pass sequence -> buffer t & 1, one TMA tensor load issued by lane 0
-    auto issue_load = [&](unsigned t, long first_unit) {
-        if (lane == 0) {
-            const unsigned bar = smem_u32(bars + (t & 1));
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::BOX_BYTES) : "memory");
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         :: "r"(smem_u32(wb + (t & 1) * C::BOX)), "l"(reinterpret_cast<unsigned long long>(&ta.tmP)),
-                            "r"((int)first_unit), "r"(0), "r"(bar) : "memory");
-        }
-    };
-    auto claim_group = [&]() -> long {
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
-        return (long)__shfl_sync(0xffffffffu, g, 0);
-    };
-    unsigned t = 0;                                 // passes done by this warp (buffer and mbarrier phase bookkeeping)
-    for (long g = claim_group(); g < ngroups; g = claim_group()) {
-        // the first pass's box lands behind phase A (both buffers are free here: the stores of the previous group have
-        // been waited for in its last pass ... except the very last one)
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        issue_load(t, g * 32);
-        // ---------------- phase A: lane = filter ------------------------------------------------------------
-        {
-            const long unit = g * 32 + lane;
-            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
-            double x[13], u[3], f[13];
-#pragma unroll
-            for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
-            {
-                SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
-                model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
-            }
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
-            if (unit < a.B) {
-#pragma unroll
-                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
-            }
-        }
-        __syncwarp();
-        // ---------------- phase B: 8 lanes = filter, 4 filters per pass -------------------------------------
-#pragma unroll 1
-        for (int p = 0; p < 8; ++p, ++t) {
-            const double* __restrict__ T = Jt + p * C::PS + lu;
-            double* const box = reinterpret_cast<double*>(wb + (t & 1) * C::BOX) + lu;
-            double p0[13], p1[13], n0[13], n1[13];
-            mbar_wait(bars + (t & 1), (t >> 1) & 1);
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {              // rows r0, r1 of P
-                p0[k] = box[(r0 * 13 + k) * 4];
-                p1[k] = v1 ? box[(r1 * 13 + k) * 4] : 0.0;
-            }
-            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {              // rows r0, r1 of Q = P A^T, in place
-                box[(r0 * 13 + k) * 4] = fma(a.dt, n0[k], p0[k]);
-                if (v1) box[(r1 * 13 + k) * 4] = fma(a.dt, n1[k], p1[k]);
-            }
-            __syncwarp();
-            // half a pass after the previous pass's store was issued: its buffer has been read, the next box may land in it
-            if (p < 7) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                issue_load(t + 1, g * 32 + (p + 1) * 4);
-            }
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {              // columns r0, r1 of Q
-                p0[k] = box[(k * 13 + r0) * 4];
-                p1[k] = v1 ? box[(k * 13 + r1) * 4] : 0.0;
-            }
-            ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
-#pragma unroll
-            for (int i = 0; i < 13; ++i) {              // columns r0, r1 of Pn = A Q + W, in place
-                box[(i * 13 + r0) * 4] = fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0];
-                if (v1) box[(i * 13 + r1) * 4] = fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1];
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {                            // filters >= B are clipped by the tensor map
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                             :: "l"(reinterpret_cast<unsigned long long>(&ta.tmPn)), "r"((int)(g * 32 + p * 4)), "r"(0),
-                                "r"(smem_u32(wb + (t & 1) * C::BOX)) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-        __syncwarp();                                   // phase B is done with the Jacobian tile before the next group
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // EKF measurement update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125), thread per filter, out of place for P:

@@ -43,7 +43,7 @@ static encode_tiled_fn encode_tiled() {
     }
     return fn;
 }
-// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][4 units].  False when the layout does not
+// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][8 units].  False when the layout does not
 // meet the TMA constraints (16-byte aligned base and pitch; an even B, because the TMA clips out-of-range columns in
 // 16-byte units and an odd B would spill one double into the padding): the caller then uses the direct-store kernel.
 bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows) {
@@ -51,7 +51,7 @@ bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int ro
     if (!enc || !base || B <= 0 || (B & 1) || B >= (1L << 31) || ((uintptr_t)base & 15) || ((ld * 8) & 15) || ld * 8 >= (1L << 40)) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {4, (cuuint32_t)rows};
+    const cuuint32_t box[2] = {8, (cuuint32_t)rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
