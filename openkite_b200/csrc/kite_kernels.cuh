@@ -571,20 +571,24 @@ struct EkfArgs {
     unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
 };
 template <bool ARM> struct EfCfg {
-    static constexpr int WARPS = ARM ? 5 : 6;                         // shared memory bound: 35 / 40 KB per warp
-    static constexpr int NS = ARM ? JAC_SLOTS : JAC_SLOTS_NOARM;
+    // state-Jacobian slots only (the EKF needs no Ju), numbered as in the sensitivity kernel (repeated +-q/2 entries share
+    // a slot): 99 without a tether arm, so that SEVEN warps' tiles and transpose buffers fit one SM
+    static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM - 7;
     // pass stride == 4 (mod 16) doubles: the 8 four-lane groups of a phase-A store land in distinct bank octets
     static constexpr int PS = NS * 4 + ((NS * 4) % 16 == 12 ? 8 : ((NS * 4) % 16 == 0 ? 4 : (20 - (NS * 4) % 16) % 16));
     static constexpr int QR = 15;                                     // transpose buffer row stride (odd: conflict-free rows)
     static constexpr int QS = 4 * 13 * QR;                            // transpose buffer [4 filters][13][QR]
-    static constexpr int PER_WARP = 8 * PS + QS + 172;                // doubles (+ W, 13 x 13, padded)
-    static constexpr size_t SMEM = sizeof(double) * WARPS * PER_WARP;
+    static constexpr int PER_WARP = 8 * PS + QS;                      // doubles
+    static constexpr int WARPS = (int)((SF_SMEM_MAX - 176 * sizeof(double)) / (sizeof(double) * PER_WARP)) < 8
+                                     ? (int)((SF_SMEM_MAX - 176 * sizeof(double)) / (sizeof(double) * PER_WARP)) : 8;
+    static constexpr size_t SMEM = sizeof(double) * (WARPS * PER_WARP + 176);      // + W (13 x 13, one copy per CTA)
 };
+static_assert(make_sens_tab().jx[12][12] == SENS_SLOTS_NOARM - 8, "state-Jacobian slots come first");
 static_assert(EfCfg<false>::PS % 16 == 4 && EfCfg<true>::PS % 16 == 4, "bank-conflict-free pass stride");
 
 struct SmemSink {       // compact slots of this lane's filter in the warp's shared tile
     double* base;       // &Jt[lane / 4][0][lane % 4]
-    __device__ __forceinline__ void jx(int i, int j, double v) const { base[jx_slot(i, j) * 4] = v; }
+    __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 4] = v; }
     __device__ __forceinline__ void ju(int, int, double) const {}     // the EKF uses the state Jacobian only
 };
 
@@ -599,7 +603,7 @@ __device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, cons
 #pragma unroll
         for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
             if (jx_nz(i, j, ARM)) {
-                const double jv = T[jx_slot(i, j) * 4];
+                const double jv = T[SENS_TAB.jx[i][j] * 4];
                 y0[i] = fma(jv, v0[j], y0[i]);
                 y1[i] = fma(jv, v1[j], y1[i]);
             }
@@ -614,13 +618,13 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* const Jt = reinterpret_cast<double*>(smem_raw) + (size_t)warp * C::PER_WARP;
     double* const Qt = Jt + 8 * C::PS;
-    double* const Ws = Qt + C::QS;                 // the warp's copy of W (13 x 13 row-major)
+    double* const Ws = reinterpret_cast<double*>(smem_raw) + (size_t)C::WARPS * C::PER_WARP;   // W (13 x 13 row-major), one copy per CTA
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
     const int r0 = 2 * l, r1 = 2 * l + 1;          // rows of P (phase B, first product) = columns of Pn (second product)
     const bool v0 = r0 < 13, v1 = r1 < 13;
-    for (int t = lane; t < 169; t += 32) Ws[t] = __ldg(a.W + t);
-    __syncwarp();
+    for (int t = threadIdx.x; t < 169; t += blockDim.x) Ws[t] = __ldg(a.W + t);
+    __syncthreads();
     // rows r0, r1 of P for the 4 filters of a pass (registers; issued one pass ahead so the loads fly behind the FMAs)
     auto load_rows = [&](long g, int p, double (&q0)[13], double (&q1)[13]) {
         const long unit = g * 32 + p * 4 + lu;
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
         }
     };
 
-    // groups are claimed from a global counter: 6 warps sit on 4 schedulers and do not all run at the same speed
+    // groups are claimed from a global counter: 7 warps sit on 4 schedulers and do not all run at the same speed
     auto claim_group = [&]() -> long {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.next_group, 1ULL);

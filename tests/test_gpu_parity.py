@@ -116,6 +116,35 @@ def test_tether_arm_golden(okb, params, golden):
     e.close()
 
 
+def test_tether_arm_batch_vs_oracle(okb, params, yaml_path):
+    """Tether-arm model (21 extra Jacobian entries, its own kernel instantiations): ragged batches against the oracle, both
+    through the TMA-output path (even B) and the direct-store path (odd B); EKF predict with the arm as well."""
+    from oracle.oracle_py import Oracle, params_from_yaml, PARAM_FIELDS
+    arm = [0.012, -0.004, 0.021]
+    p2 = okb.KiteParams.from_buffer_copy(params)
+    p2.rx, p2.ry, p2.rz = arm
+    prm = params_from_yaml(yaml_path)
+    for key, v in zip(("rx", "ry", "rz"), arm):
+        prm[PARAM_FIELDS.index(("tether", key))] = v
+    orc = Oracle(prm)
+    e = okb.Engine(p2, okb.KITE)
+    h = 0.02
+    for B in (330, 77):
+        x = orc.synth_x0(9, B); u = orc.synth_controls(9, B, 1)[:, 0, :]
+        xn, Phi, Gam = e.sens_step(soa(x), soa(u), h)
+        rxn, rPhi, rGam = orc.rk4_sens(x, u, h)
+        assert_close(aos(xn), rxn, RTOL, what="arm xn B=%d" % B)
+        assert_close(aos(Phi, 13, 13), rPhi, RTOL, what="arm Phi B=%d" % B)
+        assert_close(aos(Gam, 13, 3), rGam, RTOL, what="arm Gamma B=%d" % B)
+        W, _ = orc.ekf_defaults()
+        P = np.tile(10 * W, (B, 1, 1))
+        xe, Pe = e.ekf_predict(soa(x), soa(u), 0.0084, soa(P), W)
+        rxe, rPe = orc.ekf_predict(x, u, 0.0084, P, W)
+        assert_close(aos(xe), rxe, RTOL, what="arm EKF xn B=%d" % B)
+        assert_close(aos(Pe, 13, 13), rPe, RTOL, what="arm EKF Pn B=%d" % B)
+    e.close()
+
+
 def test_identification_variant_golden(okb, params, golden):
     e = okb.Engine(params, okb.KITE_ID)
     for n, c in golden["rhs_id"].items():
