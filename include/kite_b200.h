@@ -134,8 +134,11 @@ int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, doubl
  *   xn = RK4(x,u,h), Phi = d xn/d x (13x13), Gamma = d xn/d u (13x3).
  * Replaces: SX::jacobian chained through rk4_symbolic (kite.cpp:327,337; MATLAB RK4_JACOBIAN kite_sim.m:300-301).
  *   x_d [13][ld], u_d [3][ld], xn_d [13][ld], Phi_d [169][ld], Gamma_d [39][ld]
- *   work_d: device scratch of AT LEAST kite_rk4_sens_work_bytes(B) bytes (stage Jacobians of the resident warps of the
- *           persistent kernel; independent of B beyond one wave: ~120 MB on a B200). */
+ *   work_d: device scratch of AT LEAST kite_rk4_sens_work_bytes(B) bytes (stage states of the resident warps of the
+ *           persistent kernel, 16 KB per warp; independent of B beyond one wave: ~19 MB on a B200.  The stage Jacobians
+ *           themselves never leave shared memory).
+ *   Phi_d / Gamma_d are written by TMA tensor stores when their base and pitch are 16-byte aligned (even ld) and B is
+ *   even, by ordinary stores otherwise: same values either way. */
 size_t kite_rk4_sens_work_bytes(long B);
 int kite_rk4_sens_step(kite_ctx* ctx, long B, long ld, double h, const double* x_d, const double* u_d, double* xn_d,
                        double* Phi_d, double* Gamma_d, void* work_d);
