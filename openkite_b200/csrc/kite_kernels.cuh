@@ -312,11 +312,13 @@ template <bool ARM> struct SfCfg {
     // a warp's tiles are laid out [pass][stage]; the pass stride is == 8 (mod 16) doubles so that the four (stage, pass)
     // groups of a half-warp store still land in distinct bank octets
     static constexpr int PASS_S = 4 * TILE_S + 8;
-    static constexpr size_t SMEM_PER_WARP = sizeof(double) * 2 * PASS_S;
-    static constexpr int FIT = (int)((SF_SMEM_MAX - 2048) / SMEM_PER_WARP);
+    // per-warp stride: a multiple of 512 bytes, so that the TMA's 64-byte swizzle (a function of address bits 7..8) is
+    // the same for every warp's output boxes
+    static constexpr size_t SMEM_PER_WARP = (sizeof(double) * 2 * PASS_S + 511) / 512 * 512;
+    static constexpr int FIT = (int)((SF_SMEM_MAX - 4096) / SMEM_PER_WARP);
     static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
     static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
-    static constexpr size_t SMEM = SMEM_TILES + sizeof(unsigned) * 13 * 32;       // + gather table
+    static constexpr size_t SMEM = SMEM_TILES + 2 * sizeof(unsigned) * 13 * 32;   // + gather table, staging table
     // TMA output: the [169][8] and [39][8] boxes of a ROUND (both passes) are staged in pass 0's tiles, all four dead once
     // pass 0 has consumed them (bytes from the warp's base, 128-byte aligned).  The [169] box runs over the zero row of
     // pass 0's stage-1 tile, which is restored after the TMA has read the box.
@@ -345,9 +347,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     double* const tile = reinterpret_cast<double*>(smem_raw + (size_t)warp * C::SMEM_PER_WARP);
     double* const Sw = a.Sw + ((long)blockIdx.x * C::WARPS + warp) * SF_SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
-    // phase B: lane = (column pair l, unit lu of the pass) with the unit in the LOW lane bits, so that a half-warp store
-    // into the output box covers 4 rows x 4 units (2-way bank conflicts at the box's 64-byte row pitch instead of 4-way)
-    const int lu = lane & 3, l = lane >> 2;
+    // phase B: 8 consecutive lanes = one unit, so that the 4 addresses of a Jacobian-entry load are each shared by a
+    // contiguous lane octet: ONE shared-memory wavefront per LDS.64 (with the unit in the low lane bits it takes two)
+    const int lu = lane >> 3, l = lane & 7;
     const int c0 = l, c1 = l + 8;                  // tangent columns of this lane in phase B
 
     // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
@@ -367,6 +369,23 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 if (ok && c == c1) s1 = sl;
             }
             goff[i * 32] = (unsigned)((s0 * 4 + lu) * 8) | ((unsigned)((s1 * 4 + lu) * 8) << 16);
+        }
+    }
+    // staging table (TMA output): byte offsets, from the warp's base, of row i of this lane's two output columns in the
+    // [169][8] / [39][8] boxes of a round, for pass 0 (pass 1: offset ^ 32), c0 in the low and c1 in the high half.  The
+    // boxes use the TMA's 64-byte swizzle (16-byte chunk index ^= address bits 7..8), so the eight rows of a half-warp
+    // store land in eight different 16-byte bank groups: conflict free instead of 4-way at the dense 64-byte row pitch.
+    unsigned* const soff = reinterpret_cast<unsigned*>(smem_raw + C::SMEM_TILES) + 13 * 32 + lane;
+    if (TMA_OUT && warp == 0) {
+        const unsigned base_abs = (unsigned)__cvta_generic_to_shared(smem_raw);
+#pragma unroll
+        for (int i = 0; i < 13; ++i) {
+            const unsigned log0 = (unsigned)C::BOX_PHI + (unsigned)(i * 13 + c0) * 64u + (unsigned)lu * 8u;
+            const unsigned log1 = (c1 < 13) ? (unsigned)C::BOX_PHI + (unsigned)(i * 13 + c1) * 64u + (unsigned)lu * 8u
+                                            : (unsigned)C::BOX_GAM + (unsigned)(i * 3 + c1 - 13) * 64u + (unsigned)lu * 8u;
+            const unsigned ph0 = log0 ^ ((((base_abs + log0) >> 7) & 3u) << 4);
+            const unsigned ph1 = log1 ^ ((((base_abs + log1) >> 7) & 3u) << 4);
+            soff[i * 32] = ph0 | (ph1 << 16);
         }
     }
     __syncthreads();
@@ -507,16 +526,15 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                     // of 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by the
                     // tensor map
                     unsigned char* const wb = smem_raw + (size_t)warp * C::SMEM_PER_WARP;
-                    double* const bphi = reinterpret_cast<double*>(wb + C::BOX_PHI);
-                    double* const bgam = reinterpret_cast<double*>(wb + C::BOX_GAM);
-                    double* const o0 = bphi + c0 * 8 + p * 4 + lu;
-                    double* const o1 = ((c1 < 13) ? bphi + c1 * 8 : bgam + (c1 - 13) * 8) + p * 4 + lu;
-                    const int rs1 = (c1 < 13) ? 104 : 24;
+                    unsigned char* const bphi = wb + C::BOX_PHI;
+                    unsigned char* const bgam = wb + C::BOX_GAM;
                     if (p == 0) __syncwarp();           // every lane is done with pass 0's tiles (the box lies over them)
+                    const unsigned px = p ? 32u : 0u;
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
-                        o0[i * 104] = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
-                        o1[i * rs1] = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
+                        const unsigned o = soff[i * 32] ^ (px | (px << 16));
+                        *reinterpret_cast<double*>(wb + (o & 0xffffu)) = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+                        *reinterpret_cast<double*>(wb + (o >> 16)) = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
                     }
                     if (p == 1) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -43,7 +43,7 @@ static encode_tiled_fn encode_tiled() {
     }
     return fn;
 }
-// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][8 units].  False when the layout does not
+// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][8 units], 64-byte swizzle in shared memory.  False when the layout does not
 // meet the TMA constraints (16-byte aligned base and pitch; an even B, because the TMA clips out-of-range columns in
 // 16-byte units and an odd B would spill one double into the padding): the caller then uses the direct-store kernel.
 bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows) {
@@ -54,7 +54,7 @@ bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int ro
     const cuuint32_t box[2] = {8, (cuuint32_t)rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s) {
     if (rigid) go_fused<false, true, false>(a, s);
