@@ -313,30 +313,35 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
 }
 
 // ---------------------------------------------------------------- sensitivities -------------------
-size_t kite_rk4_sens_work_bytes(long B) {
-    if (B <= 0) return 0;
-    // persistent kernel: one private [4 stages][x(13) | u(3)][32 units] line of stage states per RESIDENT warp (groups are
-    // claimed dynamically, so every warp of every launched CTA may need its line), independent of B beyond one wave.
+// workspace layout: [stage-state lines of the resident warps][per-group step counters of a rollout]
+static size_t sens_state_bytes(long B) {
+    // persistent kernel: one private [4 stages][x(13) | u(3)][32 units] line of stage states per RESIDENT warp (work items
+    // are claimed dynamically, so every warp of every launched CTA may need its line), independent of B beyond one wave.
     // The stage Jacobians themselves never leave shared memory.
     const long groups = (B + 31) / 32;
     const long warps = std::min(groups + SF_WARPS, sens_fused_max_warps());     // covers any warps-per-CTA <= SF_WARPS
     return sizeof(double) * (size_t)SF_SCRATCH_PER_WARP * (size_t)warps;
 }
+size_t kite_rk4_sens_work_bytes(long B) {
+    if (B <= 0) return 0;
+    return sens_state_bytes(B) + (sizeof(int) * (size_t)((B + 31) / 32) + 255) / 256 * 256;
+}
 
-static int sens_step_impl(kite_ctx* ctx, long B, long ld, long ldw, double h, const double* x, const double* u, double* xn,
-                          double* Phi, double* Gamma, void* work) {
+static int sens_impl(kite_ctx* ctx, long B, long ld, long N, double h, const double* x, const double* u, double* xn,
+                     double* Phi, double* Gamma, void* work) {
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemsetAsync(ctx->counters.ptr, 0, 8, ctx->stream));
     SensArgs a{};
-    a.K = ctx->K; a.B = B; a.ld = ld; a.h = h; a.x = x; a.u = u; a.xn = xn; a.Phi = Phi; a.Gamma = Gamma;
+    a.K = ctx->K; a.B = B; a.ld = ld; a.N = N; a.h = h; a.x = x; a.u = u; a.xn = xn; a.Phi = Phi; a.Gamma = Gamma;
     a.Sw = (double*)work; a.next_group = (unsigned long long*)ctx->counters.ptr;
-    (void)ldw;
+    a.done = (int*)((char*)work + sens_state_bytes(B));
+    if (N > 1) CK(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)((B + 31) / 32), ctx->stream));
     // [Phi | Gamma] leave through TMA tensor stores when the output layout allows it (16-byte aligned base and pitch:
-    // an even ld); KITE_SENS_DIRECT_STORES=1 forces the direct-store kernel (developer comparison switch)
+    // an even ld; an even B); KITE_SENS_DIRECT_STORES=1 forces the direct-store kernel (developer comparison switch)
     static const bool direct = getenv("KITE_SENS_DIRECT_STORES") && getenv("KITE_SENS_DIRECT_STORES")[0] == '1';
-    const bool tma_out = !rigid && !direct && sens_make_tensor_map(&a.tmPhi, Phi, B, ld, 169) &&
-                         sens_make_tensor_map(&a.tmGam, Gamma, B, ld, 39);
+    const bool tma_out = !rigid && !direct && sens_make_tensor_map(&a.tmPhi, Phi, B, ld, 169, N) &&
+                         sens_make_tensor_map(&a.tmGam, Gamma, B, ld, 39, N);
     launch_sens_fused(a, rigid, ctx->K.has_arm != 0, tma_out, ctx->stream);
     LAUNCH_CHECK("k_sens_fused");
     return KITE_OK;
@@ -350,7 +355,7 @@ int kite_rk4_sens_step(kite_ctx* ctx, long B, long ld, double h, const double* x
     if (!u_d && ctx->model_kind != KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_step: u_d is null");
     if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
-    return sens_step_impl(ctx, B, ld, B, h, x_d, u_d ? u_d : x_d, xn_d, Phi_d, Gamma_d, work_d);
+    return sens_impl(ctx, B, ld, 1, h, x_d, u_d ? u_d : x_d, xn_d, Phi_d, Gamma_d, work_d);
 }
 
 int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const double* x0_d, const double* u_d,
@@ -360,15 +365,9 @@ int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, cons
         return fail(ctx, KITE_ERR_ARG, "kite_rk4_sens_rollout: bad argument");
     if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
-    // The primal recurrence is sequential in k; each step's (Phi_k, Gamma_k) only depends on x_k, so the chain is
-    // N stream-ordered launches of the single-step pair, step k reading the state written by step k-1.
-    for (long k = 0; k < N; ++k) {
-        const double* xk = (k == 0) ? x0_d : xs_d + (size_t)(k - 1) * 13 * ld;
-        int rc = sens_step_impl(ctx, B, ld, B, h, xk, u_d + (size_t)k * 3 * ld, xs_d + (size_t)k * 13 * ld,
-                                Phi_d + (size_t)k * 169 * ld, Gamma_d + (size_t)k * 39 * ld, work_d);
-        if (rc != KITE_OK) return rc;
-    }
-    return KITE_OK;
+    // The primal recurrence is sequential in k, but only per trajectory: ONE launch walks the (step, group) work items
+    // in step-major order, step k of a group waiting for the state its step k - 1 has published (k_sens_fused).
+    return sens_impl(ctx, B, ld, N, h, x0_d, u_d, xs_d, Phi_d, Gamma_d, work_d);
 }
 
 // ---------------------------------------------------------------- collocation ---------------------

@@ -248,16 +248,19 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 //   No TMA, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
 // ================================================================================================
 struct SensArgs {
-    alignas(64) CUtensorMap tmPhi;    // [169][B] rows of ld doubles, box [169][8 units]  (only read by the TMA-output kernels)
-    alignas(64) CUtensorMap tmGam;    // [39][B], box [39][8 units]
+    alignas(64) CUtensorMap tmPhi;    // [N][169][B] rows of ld doubles, box [1][169][8 units]  (only read by the TMA-output kernels)
+    alignas(64) CUtensorMap tmGam;    // [N][39][B], box [1][39][8 units]
     KiteConsts K;
     long B, ld;
+    long N;                           // steps of the multiple-shooting rollout (1: a single step)
     double h;
-    const double* x; const double* u;
-    double* xn; double* Phi; double* Gamma;
+    const double* x; const double* u; // x [13][ld] (state before step 0), u [N][3][ld]
+    double* xn; double* Phi; double* Gamma;   // xn [N][13][ld] (state after each step), Phi [N][169][ld], Gamma [N][39][ld]
     double* Sw;     // scratch: [resident warp][4 stages][16 = x(13) | u(3)][32 units]
-    unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
+    unsigned long long* next_group;   // device counter (zeroed before the launch): work items are handed out dynamically
+    int* done;      // [groups] steps finished per group (zeroed before the launch; only used when N > 1)
 };
+
 
 // ---- compact slots of the sensitivity tile ------------------------------------------------------------------
 // As SLOT_TAB, but the 12 entries d q_dot / d w = {+-q/2} (kite_model.cuh, Qw) that repeat a value WITH ITS SIGN share a
@@ -393,32 +396,47 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     // Groups are claimed from a global counter instead of a fixed stride: warps that share a scheduler run at different
     // speeds, and a static split would leave the fast ones idle at the end.  The next group's input lines are pulled
     // into L2 while this one is computed (register free).
-    auto claim_group = [&]() -> long {
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if ((long)g < ngroups) {
-            const long first = (long)g * 32;
+    // work item t = step * ngroups + group, claimed from a global counter in step-major order
+    const long nitems = ngroups * a.N;
+    auto claim_item = [&]() -> long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.next_group, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long)t < nitems) {
+            const long kk = (long)t / ngroups, first = ((long)t - kk * ngroups) * 32;
             const int row = lane >> 1;                                  // 13 rows of x, 3 of u, 2 x 128 B each
-            const double* p = (row < 13 ? a.x + (long)row * a.ld : a.u + (long)(row - 13) * a.ld) + first + (lane & 1) * 16;
-            if (first + (lane & 1) * 16 < a.B) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+            // step 0 reads x, later steps read the state their predecessor has just written (in L2 anyway)
+            const double* p = (row < 13 ? (kk == 0 ? a.x + (long)row * a.ld : nullptr)
+                                        : a.u + (kk * 3 + (row - 13)) * a.ld);
+            if (p && first + (lane & 1) * 16 < a.B) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + first + (lane & 1) * 16));
         }
-        return (long)g;
+        return (long)t;
     };
-    long g = claim_group();
+    long item = claim_item();
     __syncwarp();
 
-    while (g < ngroups) {
-        const long g_next = claim_group();
+    while (item < nitems) {
+        const long item_next = claim_item();
+        const long ks = item / ngroups, g = item - ks * ngroups;        // step, group
+        const double* const xin = (ks == 0) ? a.x : a.xn + (ks - 1) * 13 * a.ld;
+        const double* const uin = a.u + ks * 3 * a.ld;
+        double* const xout = a.xn + ks * 13 * a.ld;
+        if (ks > 0) {                                                   // the group's previous step has published its state
+            if (lane == 0) {
+                int v;
+                do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.done + g) : "memory"); } while (v < (int)ks);
+            }
+            __syncwarp();
+        }
         // ---------------- step 1: lane = unit, primal RK4 step -------------------------------------------------
         {
             const long unit = g * 32 + lane;
             const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last unit, store nothing
             double x[13], u[3], k[13], xt[13], acc[13];
 #pragma unroll
-            for (int c = 0; c < 13; ++c) { x[c] = __ldcs(a.x + (long)c * a.ld + ui); xt[c] = x[c]; }
+            for (int c = 0; c < 13; ++c) { x[c] = __ldcg(xin + (long)c * a.ld + ui); xt[c] = x[c]; }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { u[c] = RIGID ? 0.0 : __ldcs(a.u + (long)c * a.ld + ui); __stcg(Sw + (13 + c) * 32 + lane, u[c]); }
+            for (int c = 0; c < 3; ++c) { u[c] = RIGID ? 0.0 : __ldcs(uin + (long)c * a.ld + ui); __stcg(Sw + (13 + c) * 32 + lane, u[c]); }
             NoSink ns;
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
@@ -435,7 +453,12 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
             }
             if (unit < a.B) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, fma(h6, acc[c], x[c]));
+                for (int c = 0; c < 13; ++c) __stcg(xout + (long)c * a.ld + unit, fma(h6, acc[c], x[c]));
+            }
+            if (a.N > 1) {                              // publish: step ks of this group is done (release after every lane's stores)
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.done + g), "r"((int)ks + 1) : "memory");
             }
         }
         __syncwarp();                                   // the stage states of all 32 units are visible to the warp
@@ -541,19 +564,19 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                         __syncwarp();
                         if (lane == 0) {
                             const int ux = (int)(g * 32 + r * 8);
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmPhi)), "r"(ux), "r"(0),
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmPhi)), "r"(ux), "r"(0), "r"((int)ks),
                                             "r"((unsigned)__cvta_generic_to_shared(bphi)) : "memory");
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmGam)), "r"(ux), "r"(0),
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                         :: "l"(reinterpret_cast<unsigned long long>(&a.tmGam)), "r"(ux), "r"(0), "r"((int)ks),
                                             "r"((unsigned)__cvta_generic_to_shared(bgam)) : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
                 } else if (unit < a.B) {
                     // [Phi | Gamma] = E + h/6 A: row i of this lane's two columns; a warp store covers 8 rows x 4 units (32 B)
-                    double* const o0 = (c0 < 13) ? a.Phi + (long)c0 * a.ld + unit : a.Gamma + (long)(c0 - 13) * a.ld + unit;
-                    double* const o1 = (c1 < 13) ? a.Phi + (long)c1 * a.ld + unit : a.Gamma + (long)(c1 - 13) * a.ld + unit;
+                    double* const o0 = (c0 < 13) ? a.Phi + (ks * 169 + c0) * a.ld + unit : a.Gamma + (ks * 39 + c0 - 13) * a.ld + unit;
+                    double* const o1 = (c1 < 13) ? a.Phi + (ks * 169 + c1) * a.ld + unit : a.Gamma + (ks * 39 + c1 - 13) * a.ld + unit;
                     const long r0 = (c0 < 13 ? 13 : 3) * a.ld, r1 = (c1 < 13 ? 13 : 3) * a.ld;
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
@@ -565,7 +588,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #endif
             __syncwarp();                               // every lane is done reading the tile before the next round
         }
-        g = g_next;
+        item = item_next;
     }
     if (TMA_OUT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

@@ -9,6 +9,8 @@ static void go_fused(const SensArgs& a, cudaStream_t s) {
         cudaFuncSetAttribute(k_sens_fused<ARM, RIGID, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
         configured = true;
     }
+    // one warp per group at most: the steps of a group depend on each other, and the scratch (kite_rk4_sens_work_bytes)
+    // holds one line per resident warp of a grid sized by the GROUP count
     const long ngroups = (a.B + 31) / 32;
     constexpr int W = SfCfg<ARM>::WARPS;
     const long want = (ngroups + W - 1) / W;
@@ -43,17 +45,20 @@ static encode_tiled_fn encode_tiled() {
     }
     return fn;
 }
-// Tensor map of a [rows][B] FP64 matrix with row pitch ld doubles, box = [rows][8 units], 64-byte swizzle in shared memory.  False when the layout does not
-// meet the TMA constraints (16-byte aligned base and pitch; an even B, because the TMA clips out-of-range columns in
-// 16-byte units and an odd B would spill one double into the padding): the caller then uses the direct-store kernel.
-bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows) {
+// Tensor map of an [N][rows][B] FP64 array with row pitch ld doubles, box = [1][rows][8 units], 64-byte swizzle in shared
+// memory.  False when the layout does not meet the TMA constraints (16-byte aligned base and pitch; an even B, because the
+// TMA clips out-of-range columns in 16-byte units and an odd B would spill one double into the padding): the caller then
+// uses the direct-store kernel.
+bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows, long N) {
     encode_tiled_fn enc = encode_tiled();
-    if (!enc || !base || B <= 0 || (B & 1) || B >= (1L << 31) || ((uintptr_t)base & 15) || ((ld * 8) & 15) || ld * 8 >= (1L << 40)) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {8, (cuuint32_t)rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (!enc || !base || B <= 0 || N <= 0 || (B & 1) || B >= (1L << 31) || N >= (1L << 31) || ((uintptr_t)base & 15) || ((ld * 8) & 15) ||
+        (double)ld * 8 * rows * (N > 1 ? 1 : 0) >= (double)(1L << 40) || ld * 8 >= (1L << 40))
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)B, (cuuint64_t)rows, (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)rows};
+    const cuuint32_t box[3] = {8, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s) {

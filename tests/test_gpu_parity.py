@@ -308,6 +308,15 @@ def test_sens_scratch_stays_inside_work_bytes(eng, oracle):
             eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, B, B, 0.01, p(xd), p(ud), p(xn), p(Phi), p(Gam), p(buf)))
             assert float((buf[nbytes // 8:] + 3.0).abs().max()) == 0.0, "scratch overrun"
             assert_close(aos(Phi, 13, 13), rPhi, RTOL, what="Phi B=%d" % B)
+        # the single-launch rollout (many more work items than groups) must stay inside the same workspace
+        N = 7
+        x0, uu = eng.synth_inputs(B, N)
+        xs, Ps, Gs = eng.empty(N, 13, B), eng.empty(N, 169, B), eng.empty(N, 39, B)
+        eng._ck(eng.L.kite_rk4_sens_rollout(eng.ctx, B, B, N, 0.01, p(x0), p(uu), p(xs), p(Ps), p(Gs), p(buf)))
+        torch.cuda.synchronize()
+        assert float((buf[nbytes // 8:] + 3.0).abs().max()) == 0.0, "scratch overrun (rollout)"
+        ref = eng.sens_rollout(x0, uu, 0.01)
+        assert torch.equal(xs, ref[0]) and torch.equal(Ps, ref[1]) and torch.equal(Gs, ref[2])
 
 
 def test_sens_tma_output_matches_direct_stores(eng, oracle):
@@ -337,6 +346,22 @@ def test_sens_tma_output_matches_direct_stores(eng, oracle):
             assert_close(aos(xn[:, :B]), rxn, RTOL, what="xn B=%d ld=%d" % (B, ld))
             res.append((Phi[:, :B].clone(), Gam[:, :B].clone()))
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), "TMA and direct-store outputs differ"
+
+
+def test_sens_rollout_single_launch_equals_chained_steps(eng, oracle):
+    """kite_rk4_sens_rollout walks all (step, group) work items in ONE launch, step k of a group waiting for the state
+    its step k - 1 published: the result must be bitwise what N chained single-step calls give, for batches smaller and
+    larger than one wave of the persistent grid and for TMA-eligible and odd sizes."""
+    h = 0.02
+    for B, N in ((40000, 6), (4099, 9), (64, 25)):
+        x0, u = eng.synth_inputs(B, N)
+        xs, Phi, Gam = eng.sens_rollout(x0, u, h)
+        xk = x0
+        for k in range(N):
+            xn, P1, G1 = eng.sens_step(xk, u[k].contiguous(), h)
+            assert torch.equal(xn, xs[k]) and torch.equal(P1, Phi[k]) and torch.equal(G1, Gam[k]), "step %d of B=%d" % (k, B)
+            xk = xn
+        assert bool(torch.isfinite(Phi).all())
 
 
 def test_sens_linearity_property(eng, oracle):
