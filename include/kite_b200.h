@@ -142,8 +142,11 @@ int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, doubl
 size_t kite_rk4_sens_work_bytes(long B);
 int kite_rk4_sens_step(kite_ctx* ctx, long B, long ld, double h, const double* x_d, const double* u_d, double* xn_d,
                        double* Phi_d, double* Gamma_d, void* work_d);
-/* Multiple-shooting rollout: B trajectories x N steps, chained primal, per-step sensitivities.
- *   x0_d [13][ld], u_d [N][3][ld]; xs_d [N][13][ld] (state after each step), Phi_d [N][169][ld], Gamma_d [N][39][ld] */
+/* Multiple-shooting rollout: B trajectories x N steps, chained primal, per-step sensitivities, ONE kernel launch for the
+ * whole horizon (the (step, group-of-32) work items are walked in step-major order; results are bitwise those of N
+ * chained kite_rk4_sens_step calls).
+ *   x0_d [13][ld], u_d [N][3][ld]; xs_d [N][13][ld] (state after each step), Phi_d [N][169][ld], Gamma_d [N][39][ld]
+ *   work_d: kite_rk4_sens_work_bytes(B) bytes, as for the single step (it includes the per-group step counters). */
 int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const double* x0_d, const double* u_d,
                           double* xs_d, double* Phi_d, double* Gamma_d, void* work_d);
 
