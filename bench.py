@@ -259,6 +259,17 @@ def main():
         out["rk4_sens"] = {"kernel": "k_sens_fused", "units": Bs, "ms": ms, "state_steps_per_s": Bs / (ms * 1e-3), "achieved_tflops": tf,
                            "frac_of_measured_peak": tf / fp64_peak, "flops_per_unit": FLOPS_RK4_SENS_STEP,
                            "hbm_gbs_out": (169 + 39 + 13) * 8.0 * Bs / (ms * 1e-3) / 1e9}
+        # config 3 shape: 100k trajectories x NMPC horizon (20 steps), chained primal + per-step [Phi | Gamma], one launch
+        Br, Nr = min(B, 100000), min(N, 20)
+        if Br >= 1024 and Nr >= 2:
+            xr, ur = x0[:, :Br].contiguous(), u[:Nr, :, :Br].contiguous()
+            ro = (eng.empty(Nr, 13, Br), eng.empty(Nr, 169, Br), eng.empty(Nr, 39, Br))
+            ms = timed(lambda: eng.sens_rollout(xr, ur, 0.02, out=ro), 5)
+            tf = FLOPS_RK4_SENS_STEP * Br * Nr / (ms * 1e-3) / 1e12
+            out["rk4_sens_rollout"] = {"kernel": "k_sens_fused (one launch per horizon)", "trajectories": Br, "steps": Nr, "ms": ms,
+                                       "state_steps_per_s": Br * Nr / (ms * 1e-3), "achieved_tflops": tf,
+                                       "frac_of_measured_peak": tf / fp64_peak}
+            del xr, ur, ro
         import numpy as np
         Wd = np.diag(np.array([.5, .5, .5, .5, .5, .5, .5, .1, .1, .01, .05, .05, .05]) ** 2)     # kiteEKF.cpp:6-13
         Pe = torch.from_numpy((10 * Wd).reshape(169, 1)).to(dev).expand(169, Bs).contiguous()
