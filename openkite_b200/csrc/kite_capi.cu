@@ -77,6 +77,7 @@ struct kite_ctx {
     long long launches = 0;
     DevBuf small;                        // W / V / compD staging
     DevBuf scratch;                      // ekf update out-of-place P
+    DevBuf ekf_lines;                    // ekf predict: pre-step state lines of the resident warps (TMA kernel)
     DevBuf pipe[2];                      // host-pipeline chunk buffers
     DevBuf shared_u, shared_y;
     DevBuf node_w;                       // collocated-cost node weights
@@ -120,7 +121,7 @@ int kite_destroy(kite_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
-    ctx->small.release(); ctx->scratch.release(); ctx->pipe[0].release(); ctx->pipe[1].release();
+    ctx->small.release(); ctx->scratch.release(); ctx->ekf_lines.release(); ctx->pipe[0].release(); ctx->pipe[1].release();
     ctx->shared_u.release(); ctx->shared_y.release(); ctx->node_w.release(); ctx->counters.release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
@@ -449,7 +450,8 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     CK(cudaMemsetAsync((char*)ctx->counters.ptr + 8, 0, 8, ctx->stream));
     EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
               (unsigned long long*)((char*)ctx->counters.ptr + 8)};
-    launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, ctx->stream);
+    if (ctx->ekf_lines.reserve(ekf_predict_scratch_bytes())) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
+    launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, (double*)ctx->ekf_lines.ptr, ctx->stream);
     LAUNCH_CHECK("k_ekf_predict");
     return KITE_OK;
 }

@@ -742,6 +742,206 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
     }
 }
 
+// ================================================================================================
+// EKF predict, round-based with TMA boxes (the product path when the covariance layout is TMA-addressable: 16-byte
+// aligned base and pitch, even B).  Same arithmetic as k_ekf_predict; what changes is how P moves and how much of the
+// Jacobian is in flight.  A warp owns groups of 32 filters:
+//   step 1 (lane = filter): RK4 step -> xn; the pre-step state and the control are parked in the warp's L2-resident line.
+//   four rounds of 8 filters:
+//     Jacobian at the pre-step state with lane = (filter, replica): the four replicas of a filter compute the same
+//       entries and replica 0 writes them (the evaluation costs the same issue slots for 8 or 32 active lanes; what it
+//       buys is a 6 KB tile [pass][slot][4 filters] instead of 26 KB, i.e. room for the covariance boxes);
+//     the [169][8 filters] box of P (64-byte rows, 64-byte swizzle) arrives by ONE TMA tensor load issued half a round
+//       ahead; phase B (8 lanes = filter, 2 passes of 4 filters) reads the rows of P from the box, writes Q = P A^T back
+//       IN PLACE (a lane only overwrites what it read), reads the columns of Q from the same box (the box is the
+//       transpose buffer), writes the columns of Pn = A Q + W in place, and the box leaves by ONE TMA tensor store.
+//   The LSU sees conflict-free shared accesses through per-lane offset tables instead of 52 eight-sector global accesses
+//   with 64-bit address arithmetic per pass (profiles/r1zb_ekf_before_ncu_summary.txt: LSU data pipe 63 % busy).
+// ================================================================================================
+struct EkfTmaArgs {
+    alignas(64) CUtensorMap tmP;      // [1][169][B] rows of ld doubles, box [1][169][8 filters], 64-byte swizzle
+    alignas(64) CUtensorMap tmPn;
+    EkfArgs e;
+    double* Xw;                       // scratch: [resident warp][x(13) | u(3)][32 filters]
+};
+constexpr long ET_SCRATCH_PER_WARP = 16L * 32;
+template <bool ARM> struct EtCfg {
+    static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM - 7;          // state-Jacobian slots (no Ju)
+    static constexpr int TILE_S = NS * 4;                                         // doubles per pass tile [slot][4 filters]
+    static constexpr size_t BOX = (169 * 64 + 511) / 512 * 512;                   // 10816 -> 11264: both boxes see the same swizzle
+    static constexpr unsigned BOX_BYTES = 169 * 64;
+    static constexpr size_t PER_WARP = (2 * BOX + sizeof(double) * 2 * TILE_S + 511) / 512 * 512;
+    static constexpr int FIT = (int)((SF_SMEM_MAX - 8192) / PER_WARP);
+    static constexpr int WARPS = FIT < 8 ? FIT : 8;
+    static constexpr size_t SMEM_WARPS = PER_WARP * WARPS;
+    static constexpr size_t OFF_W = SMEM_WARPS;                                   // W (13 x 13), one copy per CTA
+    static constexpr size_t OFF_TAB = OFF_W + sizeof(double) * 176;               // row / column offset tables [2][13][32] words
+    static constexpr size_t OFF_BAR = OFF_TAB + sizeof(unsigned) * 2 * 13 * 32;   // two mbarriers per warp
+    static constexpr size_t SMEM = OFF_BAR + sizeof(unsigned long long) * 2 * WARPS;
+};
+static_assert(EtCfg<false>::SMEM <= SF_SMEM_MAX && EtCfg<true>::SMEM <= SF_SMEM_MAX, "shared memory");
+
+struct Rep0Sink {       // compact state-Jacobian slots of this lane's filter; only replica 0 of a filter stores
+    double* base;       // &tile[filter / 4][0][filter % 4]
+    bool on;
+    __device__ __forceinline__ void jx(int i, int j, double v) const { if (on) base[SENS_TAB.jx[i][j] * 4] = v; }
+    __device__ __forceinline__ void ju(int, int, double) const {}
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <bool ARM, bool RIGID>
+__global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(const __grid_constant__ EkfTmaArgs ta) {
+    using C = EtCfg<ARM>;
+    const EkfArgs& a = ta.e;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const wb = smem_raw + (size_t)warp * C::PER_WARP;              // [box 0][box 1][Jacobian tile]
+    double* const Jt = reinterpret_cast<double*>(wb + 2 * C::BOX);
+    double* const Ws = reinterpret_cast<double*>(smem_raw + C::OFF_W);
+    unsigned* const rtab = reinterpret_cast<unsigned*>(smem_raw + C::OFF_TAB) + lane;        // rows (r0 | r1 << 16) of entry k
+    unsigned* const ctab = rtab + 13 * 32;                                                   // columns
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::OFF_BAR) + warp * 2;
+    double* const Xw = ta.Xw + ((long)blockIdx.x * C::WARPS + warp) * ET_SCRATCH_PER_WARP;
+    const long ngroups = (a.B + 31) / 32;
+    const int lu = lane >> 3, l = lane & 7;
+    const int r0 = l, r1 = l + 8;                  // rows of P (first product) = columns of Pn (second product)
+    const bool v1 = r1 < 13;
+
+    for (int t = threadIdx.x; t < 169; t += blockDim.x) Ws[t] = __ldg(a.W + t);
+    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + lane)) : "memory");
+    if (warp == 0) {
+        // byte offsets inside a box of entry (row, col) for this lane's filter of pass 0 (pass 1: ^ 32), with the TMA's
+        // 64-byte swizzle applied: 16-byte chunk index ^= address bits 7..8 (the same for every box: 512-byte strides)
+        const unsigned base_abs = smem_u32(smem_raw);
+        auto phys = [&](int row, int col) -> unsigned {
+            const unsigned lg = (unsigned)(row * 13 + col) * 64u + (unsigned)lu * 8u;
+            return lg ^ ((((base_abs + lg) >> 7) & 3u) << 4);
+        };
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            rtab[k * 32] = phys(r0, k) | (phys(v1 ? r1 : r0, k) << 16);
+            ctab[k * 32] = phys(k, r0) | (phys(k, v1 ? r1 : r0) << 16);
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // box of the warp's round `t` (filters first .. first + 7) -> buffer t & 1, one TMA tensor load issued by lane 0
+    auto issue_load = [&](unsigned t, long first) {
+        if (lane == 0) {
+            const unsigned bar = smem_u32(bars + (t & 1));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::BOX_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(wb + (t & 1) * C::BOX)), "l"(reinterpret_cast<unsigned long long>(&ta.tmP)),
+                            "r"((int)first), "r"(0), "r"(0), "r"(bar) : "memory");
+        }
+    };
+    auto claim_group = [&]() -> long {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
+        return (long)__shfl_sync(0xffffffffu, g, 0);
+    };
+    unsigned t = 0;                                 // rounds done by this warp (buffer and mbarrier phase bookkeeping)
+    long g = claim_group();
+    if (g < ngroups) issue_load(0, g * 32);
+    while (g < ngroups) {
+        const long g_next = claim_group();
+        // ---------------- step 1: lane = filter, RK4 step ---------------------------------------------------
+        {
+            const long unit = g * 32 + lane;
+            const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
+            double x[13], u[3];
+#pragma unroll
+            for (int c = 0; c < 13; ++c) { x[c] = __ldcs(a.x + (long)c * a.ld + ui); __stcg(Xw + c * 32 + lane, x[c]); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0; __stcg(Xw + (13 + c) * 32 + lane, u[c]); }
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
+            if (unit < a.B) {
+#pragma unroll
+                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r, ++t) {
+            // ---------------- Jacobian at the pre-step state of filters 8 r .. 8 r + 7 -> shared tile --------
+            {
+                const int f = lane & 7;
+                double x[13], u[3], fdum[13];
+#pragma unroll
+                for (int c = 0; c < 13; ++c) x[c] = __ldcg(Xw + c * 32 + r * 8 + f);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) u[c] = __ldcg(Xw + (13 + c) * 32 + r * 8 + f);
+                Rep0Sink sink{Jt + (f >> 2) * C::TILE_S + (f & 3), lane < 8};
+                model_eval<RIGID, true>(a.K, a.K.A, x, u, fdum, sink);
+            }
+            __syncwarp();
+            unsigned char* const box = wb + (t & 1) * C::BOX;
+            mbar_wait(bars + (t & 1), (t >> 1) & 1);
+            // ---------------- phase B: 8 lanes = filter, 2 passes of 4 filters ---------------------------------
+#pragma unroll 1
+            for (int p = 0; p < 2; ++p) {
+                const double* __restrict__ T = Jt + p * C::TILE_S + lu;
+                const unsigned px = p ? 32u : 0u;
+                double p0[13], p1[13], n0[13], n1[13];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {          // rows r0, r1 of P
+                    const unsigned o = rtab[k * 32] ^ (px | (px << 16));
+                    p0[k] = *reinterpret_cast<const double*>(box + (o & 0xffffu));
+                    p1[k] = v1 ? *reinterpret_cast<const double*>(box + (o >> 16)) : 0.0;
+                }
+                ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {          // rows r0, r1 of Q = P A^T, in place
+                    const unsigned o = rtab[k * 32] ^ (px | (px << 16));
+                    *reinterpret_cast<double*>(box + (o & 0xffffu)) = fma(a.dt, n0[k], p0[k]);
+                    if (v1) *reinterpret_cast<double*>(box + (o >> 16)) = fma(a.dt, n1[k], p1[k]);
+                }
+                __syncwarp();
+                if (p == 0) {
+                    // half a round after the previous round's store was issued: its buffer has been read out, the next
+                    // round's box may land in it (next round of this group, or round 0 of the next group)
+                    const long nfirst = (r < 3) ? g * 32 + (r + 1) * 8 : g_next * 32;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (r < 3 || g_next < ngroups) issue_load(t + 1, nfirst);
+                }
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {          // columns r0, r1 of Q
+                    const unsigned o = ctab[k * 32] ^ (px | (px << 16));
+                    p0[k] = *reinterpret_cast<const double*>(box + (o & 0xffffu));
+                    p1[k] = v1 ? *reinterpret_cast<const double*>(box + (o >> 16)) : 0.0;
+                }
+                ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+#pragma unroll
+                for (int i = 0; i < 13; ++i) {          // columns r0, r1 of Pn = A Q + W, in place
+                    const unsigned o = ctab[i * 32] ^ (px | (px << 16));
+                    *reinterpret_cast<double*>(box + (o & 0xffffu)) = fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0];
+                    if (v1) *reinterpret_cast<double*>(box + (o >> 16)) = fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1];
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {                            // filters >= B are clipped by the tensor map
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             :: "l"(reinterpret_cast<unsigned long long>(&ta.tmPn)), "r"((int)(g * 32 + r * 8)), "r"(0), "r"(0),
+                                "r"(smem_u32(box)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        g = g_next;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // EKF measurement update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125), thread per filter, out of place for P:
 //   S = H P H^T + V (7x7), K = P H^T S^-1 (13x7), x += K (z - H x), Pout = P - K H P.
 // S is inverted in place (Gauss-Jordan sweep on 49 registers; S is SPD so no pivoting), the gain K is parked in shared

@@ -10,7 +10,8 @@ void launch_synth_inputs(const SynthArgs& a, cudaStream_t s);
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s);
 bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows, long N);   // false: layout not TMA-eligible
 long sens_fused_max_warps();   // warps of the persistent fused kernel on the current device (scratch sizing)
-void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s);
+void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, cudaStream_t s);
+size_t ekf_predict_scratch_bytes();   // pre-step state lines of the resident warps of the TMA kernel (independent of B)
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
 void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s);
 void launch_colloc_cost(const CostArgs& a, cudaStream_t s);

@@ -1,3 +1,5 @@
+#include <cstdlib>
+
 #include "kite_launch.h"
 namespace kite {
 template <bool ARM, bool RIGID>
@@ -14,7 +16,39 @@ static void go_predict(const EkfArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
     k_ekf_predict<ARM, RIGID><<<grid, EfCfg<ARM>::WARPS * 32, EfCfg<ARM>::SMEM, s>>>(a);
 }
-void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, cudaStream_t s) {
+template <bool ARM, bool RIGID>
+static void go_predict_tma(const EkfTmaArgs& a, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_ekf_predict_tma<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EtCfg<ARM>::SMEM);
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long ngroups = (a.e.B + 31) / 32;
+    const long want = (ngroups + EtCfg<ARM>::WARPS - 1) / EtCfg<ARM>::WARPS;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
+    k_ekf_predict_tma<ARM, RIGID><<<grid, EtCfg<ARM>::WARPS * 32, EtCfg<ARM>::SMEM, s>>>(a);
+}
+size_t ekf_predict_scratch_bytes() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 256;
+    return sizeof(double) * (size_t)ET_SCRATCH_PER_WARP * 8 * (size_t)sms;
+}
+void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, cudaStream_t s) {
+    // the covariance moves as TMA boxes when its layout allows it (16-byte aligned base and pitch, even B);
+    // KITE_EKF_DIRECT=1 forces the direct load / store kernel (developer comparison switch)
+    static const bool direct = getenv("KITE_EKF_DIRECT") && getenv("KITE_EKF_DIRECT")[0] == '1';
+    EkfTmaArgs ta{};
+    ta.e = a; ta.Xw = lines;
+    if (!direct && lines && sens_make_tensor_map(&ta.tmP, const_cast<double*>(a.P), a.B, a.ld, 169, 1) &&
+        sens_make_tensor_map(&ta.tmPn, a.Pn, a.B, a.ld, 169, 1)) {
+        if (rigid) go_predict_tma<false, true>(ta, s);
+        else if (arm) go_predict_tma<true, false>(ta, s);
+        else go_predict_tma<false, false>(ta, s);
+        return;
+    }
     if (rigid) go_predict<false, true>(a, s);
     else if (arm) go_predict<true, false>(a, s);
     else go_predict<false, false>(a, s);
