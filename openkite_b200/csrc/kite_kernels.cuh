@@ -436,7 +436,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #pragma unroll
             for (int c = 0; c < 13; ++c) { x[c] = __ldcg(xin + (long)c * a.ld + ui); xt[c] = x[c]; }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { u[c] = RIGID ? 0.0 : __ldcs(uin + (long)c * a.ld + ui); __stcg(Sw + (13 + c) * 32 + lane, u[c]); }
+            for (int c = 0; c < 3; ++c) u[c] = RIGID ? 0.0 : __ldcs(uin + (long)c * a.ld + ui);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcg(Sw + (13 + c) * 32 + lane, u[c]);     // (after ALL loads: may-alias stores serialise them)
             NoSink ns;
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
@@ -861,9 +863,15 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
             double x[13], u[3];
 #pragma unroll
-            for (int c = 0; c < 13; ++c) { x[c] = __ldcs(a.x + (long)c * a.ld + ui); __stcg(Xw + c * 32 + lane, x[c]); }
+            for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0; __stcg(Xw + (13 + c) * 32 + lane, u[c]); }
+            for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
+            // (all loads before the first store: the compiler must assume the scratch aliases the inputs and would
+            // otherwise serialise load - store - load - store, one memory round trip each)
+#pragma unroll
+            for (int c = 0; c < 13; ++c) __stcg(Xw + c * 32 + lane, x[c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcg(Xw + (13 + c) * 32 + lane, u[c]);
             rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
             if (unit < a.B) {
 #pragma unroll
