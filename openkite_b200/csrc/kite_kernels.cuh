@@ -879,18 +879,29 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             }
         }
         __syncwarp();
+        // pre-step state of this lane's filter of the coming round: fetched one round ahead (the loads fly behind phase B)
+        double xq[13], uq[3];
+        {
+            const int f = lane & 7;
+#pragma unroll
+            for (int c = 0; c < 13; ++c) xq[c] = __ldcg(Xw + c * 32 + f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) uq[c] = __ldcg(Xw + (13 + c) * 32 + f);
+        }
 #pragma unroll 1
         for (int r = 0; r < 4; ++r, ++t) {
             // ---------------- Jacobian at the pre-step state of filters 8 r .. 8 r + 7 -> shared tile --------
             {
                 const int f = lane & 7;
-                double x[13], u[3], fdum[13];
-#pragma unroll
-                for (int c = 0; c < 13; ++c) x[c] = __ldcg(Xw + c * 32 + r * 8 + f);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) u[c] = __ldcg(Xw + (13 + c) * 32 + r * 8 + f);
+                double fdum[13];
                 Rep0Sink sink{Jt + (f >> 2) * C::TILE_S + (f & 3), lane < 8};
-                model_eval<RIGID, true>(a.K, a.K.A, x, u, fdum, sink);
+                model_eval<RIGID, true>(a.K, a.K.A, xq, uq, fdum, sink);
+                if (r < 3) {
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) xq[c] = __ldcg(Xw + c * 32 + (r + 1) * 8 + f);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) uq[c] = __ldcg(Xw + (13 + c) * 32 + (r + 1) * 8 + f);
+                }
             }
             __syncwarp();
             unsigned char* const box = wb + (t & 1) * C::BOX;
