@@ -364,6 +364,50 @@ def test_sens_rollout_single_launch_equals_chained_steps(eng, oracle):
         assert bool(torch.isfinite(Phi).all())
 
 
+def test_persistent_kernels_are_deterministic(eng, oracle):
+    """The persistent kernels hand out work dynamically, reuse shared-memory tiles as TMA staging boxes and (EKF) update
+    the covariance box in place: a missing fence or barrier would show up as run-to-run differences.  Repeated calls on
+    batches around the size of one wave of the grid must be bitwise identical, and the EKF's TMA path must agree bitwise
+    with nothing but itself and to 1e-9 with the direct-load kernel's layout fallback (odd pitch)."""
+    W, _ = oracle.ekf_defaults()
+    for B in (9472, 37890, 262144):
+        x0, u = eng.synth_inputs(B, 3)
+        P = torch.from_numpy((10 * W).reshape(169, 1)).cuda().expand(169, B).contiguous()
+        P = P * (1.0 + 0.01 * torch.rand(169, B, dtype=torch.float64, device="cuda"))
+        ref = None
+        for rep in range(4):
+            s1 = eng.sens_step(x0, u[0].contiguous(), 0.02)
+            s2 = eng.sens_rollout(x0, u, 0.02)
+            e1 = eng.ekf_predict(x0, u[0].contiguous(), 0.0084, P, W)
+            cur = [t.clone() for t in (*s1, *s2, *e1)]
+            if ref is None:
+                ref = cur
+            else:
+                for a_, b_ in zip(ref, cur):
+                    assert torch.equal(a_, b_), "run-to-run difference at B=%d" % B
+    # TMA path (even pitch) against the direct kernel (odd pitch) on the same filters
+    import ctypes as C
+    B = 5000
+    x0, u = eng.synth_inputs(B, 1)
+    P = torch.from_numpy((10 * W).reshape(169, 1)).cuda().expand(169, B).contiguous()
+    P = P * (1.0 + 0.01 * torch.rand(169, B, dtype=torch.float64, device="cuda"))
+    outs = []
+    for ld in (B + 2, B + 3):
+        def pad(t):
+            o = torch.zeros(t.shape[0], ld, dtype=torch.float64, device="cuda"); o[:, :B] = t; return o
+        xd, ud, Pd = pad(x0), pad(u[0]), pad(P)
+        xn = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda"); Pn = torch.full((169, ld), -7.0, dtype=torch.float64, device="cuda")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        Wh = np.ascontiguousarray(W)
+        eng._use_torch_stream()
+        eng._ck(eng.L.kite_ekf_predict_batch(eng.ctx, B, ld, 0.0084, p(xd), p(ud), p(Pd), Wh.ctypes.data_as(C.c_void_p), p(xn), p(Pn), None))
+        torch.cuda.synchronize()
+        assert float((Pn[:, B:] + 7.0).abs().max()) == 0.0, "padding written (ld=%d)" % ld
+        outs.append((xn[:, :B].clone(), Pn[:, :B].clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert_close(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), RTOL, what="EKF TMA vs direct")
+
+
 def test_sens_linearity_property(eng, oracle):
     """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
     B, h = 2048, 0.02
