@@ -462,17 +462,14 @@ int kite_ekf_update_batch(kite_ctx* ctx, long B, long ld, const double* z_d, con
     if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
     if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
-    if (ctx->scratch.reserve(sizeof(double) * 169 * (size_t)ld)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     double* Vd = (double*)ctx->small.ptr + 256;     // keep clear of W staging
     CK(cudaMemcpyAsync(Vd, V_h, sizeof(double) * 49, cudaMemcpyHostToDevice, ctx->stream));
-    EkfUpdArgs a{B, ld, z_d, P_d, x_d, (double*)ctx->scratch.ptr, Vd};
+    EkfUpdArgs a{B, ld, z_d, P_d, x_d, Vd};          // in place: no staging copy of the covariance
     launch_ekf_update(a, ctx->stream);
     LAUNCH_CHECK("k_ekf_update");
-    CK(cudaMemcpyAsync(P_d, ctx->scratch.ptr, sizeof(double) * 169 * (size_t)ld, cudaMemcpyDeviceToDevice, ctx->stream));
     return KITE_OK;
 }
 
-// ---------------------------------------------------------------- multi-GPU -----------------------
 int kite_comm_unique_id(char id_out[128]) {
     NcclApi& n = nccl_api();
     if (!n.ok() || !id_out) return KITE_ERR_NCCL;

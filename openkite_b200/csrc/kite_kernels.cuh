@@ -961,29 +961,36 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// EKF measurement update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125), thread per filter, out of place for P:
-//   S = H P H^T + V (7x7), K = P H^T S^-1 (13x7), x += K (z - H x), Pout = P - K H P.
+// EKF measurement update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125), thread per filter, IN PLACE:
+//   S = H P H^T + V (7x7), K = P H^T S^-1 (13x7), x += K (z - H x), P <- P - K H P.
 // S is inverted in place (Gauss-Jordan sweep on 49 registers; S is SPD so no pivoting), the gain K is parked in shared
-// memory ([91][block] columns, conflict free) because K (182 registers) and S^-1 (98) do not fit together, and the
+// memory ([91 + 13][block] columns, conflict free) because K (182 registers) and S^-1 (98) do not fit together, and the
 // covariance update then walks P column by column with the 7 entries of H P for that column in registers.
-// (An in-place variant saves the device-to-device copy back but loses the read-only load path: 1.65 vs 1.27 ms per 1 M.)
+// In place without a staging copy: every entry of P is read before it is written (column c is only written after all
+// reads of column c, and K only needs columns 6..12 BEFORE any write).  What made the first in-place version slow
+// (1.65 ms per 1 M filters against 1.27 ms for out-of-place + copy back) was not the missing read-only path but ordering:
+// with loads and stores on the same buffer the compiler may not hoist a load above an earlier store, so
+// "load, 7 FMAs, store" per entry became 169 dependent memory round trips.  Here each column's 20 loads are issued in
+// one batch, one column AHEAD of the stores of the previous column, and the state update is one batch at the end.
 struct EkfUpdArgs {
     long B, ld;
-    const double* z; const double* P; double* x; double* Pout;
+    const double* z; double* P; double* x;
     const double* V;         // device [49]
 };
 constexpr int EKFU_BLOCK = 128;
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_constant__ EkfUpdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* const Ks = reinterpret_cast<double*>(smem_raw) + threadIdx.x;        // K[r][c] at Ks[(r*7+c)*EKFU_BLOCK]
+    double* const Ks = reinterpret_cast<double*>(smem_raw) + threadIdx.x;        // K[r][c] at Ks[(r*7+c)*EKFU_BLOCK], dx[r] at Ks[(91+r)*EKFU_BLOCK]
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.B) return;
+    double* const P = a.P + i;
+    const long ld = a.ld;
     double S[7][7];
 #pragma unroll
     for (int r = 0; r < 7; ++r)
 #pragma unroll
-        for (int c = 0; c < 7; ++c) S[r][c] = __ldg(a.P + (long)((6 + r) * 13 + 6 + c) * a.ld + i) + __ldg(a.V + r * 7 + c);
+        for (int c = 0; c < 7; ++c) S[r][c] = P[(long)((6 + r) * 13 + 6 + c) * ld] + __ldg(a.V + r * 7 + c);
 #pragma unroll
     for (int c = 0; c < 7; ++c) {                  // in-place inverse
         const double d = 1.0 / S[c][c];
@@ -1001,12 +1008,12 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
     }
     double y[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) y[k] = __ldg(a.z + (long)k * a.ld + i) - a.x[(long)(6 + k) * a.ld + i];
+    for (int k = 0; k < 7; ++k) y[k] = __ldg(a.z + (long)k * ld + i) - a.x[(long)(6 + k) * ld + i];
 #pragma unroll 1
-    for (int r = 0; r < 13; ++r) {                 // K row r = P[r][6:13] S^-1, state update
+    for (int r = 0; r < 13; ++r) {                 // K row r = P[r][6:13] S^-1; state increment (no global store in this loop)
         double pk[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) pk[k] = __ldg(a.P + (long)(r * 13 + 6 + k) * a.ld + i);
+        for (int k = 0; k < 7; ++k) pk[k] = P[(long)(r * 13 + 6 + k) * ld];
         double dx = 0.0;
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
@@ -1016,20 +1023,40 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
             Ks[(r * 7 + c) * EKFU_BLOCK] = kv;
             dx = fma(kv, y[c], dx);
         }
-        a.x[(long)r * a.ld + i] += dx;
+        Ks[(91 + r) * EKFU_BLOCK] = dx;
     }
-#pragma unroll 1
-    for (int c = 0; c < 13; ++c) {                 // Pout[:, c] = P[:, c] - K (H P)[:, c]
-        double hp[7];
+    {                                              // x += K y: 13 loads, then 13 stores
+        double xv[13];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) hp[k] = __ldg(a.P + (long)((6 + k) * 13 + c) * a.ld + i);
+        for (int r = 0; r < 13; ++r) xv[r] = a.x[(long)r * ld + i];
+#pragma unroll
+        for (int r = 0; r < 13; ++r) a.x[(long)r * ld + i] = xv[r] + Ks[(91 + r) * EKFU_BLOCK];
+    }
+    // P[:, c] <- P[:, c] - K (H P)[:, c], column by column; column c + 1 is loaded before column c is stored
+    double hp[7], pv[13], hq[7], pq[13];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) hp[k] = P[(long)((6 + k) * 13) * ld];
+#pragma unroll
+    for (int r = 0; r < 13; ++r) pv[r] = P[(long)(r * 13) * ld];
+#pragma unroll 1
+    for (int c = 0; c < 13; ++c) {
+        if (c < 12) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) hq[k] = P[(long)((6 + k) * 13 + c + 1) * ld];
+#pragma unroll
+            for (int r = 0; r < 13; ++r) pq[r] = P[(long)(r * 13 + c + 1) * ld];
+        }
 #pragma unroll
         for (int r = 0; r < 13; ++r) {
-            double v = __ldg(a.P + (long)(r * 13 + c) * a.ld + i);
+            double v = pv[r];
 #pragma unroll
             for (int k = 0; k < 7; ++k) v = fma(-Ks[(r * 7 + k) * EKFU_BLOCK], hp[k], v);
-            a.Pout[(long)(r * 13 + c) * a.ld + i] = v;
+            P[(long)(r * 13 + c) * ld] = v;
         }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) hp[k] = hq[k];
+#pragma unroll
+        for (int r = 0; r < 13; ++r) pv[r] = pq[r];
     }
 }
 

@@ -54,7 +54,7 @@ void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, c
     else go_predict<false, false>(a, s);
 }
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s) {
-    constexpr int smem = (int)sizeof(double) * 91 * EKFU_BLOCK;
+    constexpr int smem = (int)sizeof(double) * (91 + 13) * EKFU_BLOCK;
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(k_ekf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
     k_ekf_update<0><<<blocks_for(a.B, EKFU_BLOCK), EKFU_BLOCK, smem, s>>>(a);
