@@ -10,3 +10,4 @@ ncu --set full --clock-control none --import-source on -k regex:k_rk4_rollout -s
 $CMD > gpurun_out/plain3_full_$TAG.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_sens_fused -s 5 -c 1 -o gpurun_out/prof_sens_full_$TAG $CMD > gpurun_out/ncu_sens_full_$TAG.log 2>&1
 ls -la gpurun_out/ | tail -12
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ekf_predict -s 2 -c 1 -o gpurun_out/prof_ekf_full_$TAG $CMD > gpurun_out/ncu_ekf_full_$TAG.log 2>&1
