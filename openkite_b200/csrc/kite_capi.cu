@@ -76,7 +76,7 @@ struct kite_ctx {
     std::string err;
     long long launches = 0;
     DevBuf small;                        // W / V / compD staging
-    DevBuf scratch;                      // ekf update out-of-place P
+    DevBuf scratch;                      // output of the FP64 peak microbenchmark
     DevBuf ekf_lines;                    // ekf predict: pre-step state lines of the resident warps (TMA kernel)
     DevBuf pipe[2];                      // host-pipeline chunk buffers
     DevBuf shared_u, shared_y;

@@ -18,7 +18,7 @@ namespace kite {
 // ---- compact Jacobian storage -----------------------------------------------------------------
 // Structural non-zeros of [Jx | Ju], row-major slot numbering.  The 21 entries
 // that only exist with a tether arm (rows w_dot, cols r,q) get slots too but are only touched when
-// has_arm.  JAC_SLOTS slots of [ld] doubles each.
+// has_arm.  The slot tables of the kernels (SENS_TAB) are built from these predicates.
 __host__ __device__ constexpr bool jx_nz(int i, int j, bool arm) {
     if (i < 3) return !((i == 0 && j == 3) || (i == 2 && j == 5));
     if (i < 6) return (j < 6) || arm;
@@ -31,29 +31,7 @@ __host__ __device__ constexpr bool ju_nz(int i, int j) {
            (i == 1 && j == 2) || (i == 3 && j == 2) || (i == 5 && j == 2);
 }
 constexpr int JAC_SLOTS = JX_SLOTS + 7;   // 132
-struct SlotTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
-constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7: the slots a zero-arm model touches are the first 111
-constexpr SlotTab make_slot_tab() {
-    SlotTab t{};
-    int s = 0;
-    for (int i = 0; i < 13; ++i)
-        for (int j = 0; j < 13; ++j) t.jx[i][j] = jx_nz(i, j, false) ? s++ : -1;
-    for (int i = 0; i < 13; ++i)
-        for (int j = 0; j < 3; ++j) t.ju[i][j] = ju_nz(i, j) ? s++ : -1;
-    for (int i = 0; i < 13; ++i)
-        for (int j = 0; j < 13; ++j)
-            if (jx_nz(i, j, true) && !jx_nz(i, j, false)) t.jx[i][j] = s++;
-    // slot of entry (row i, tangent column c) of [Jx | Ju]
-    for (int i = 0; i < 13; ++i)
-        for (int c = 0; c < 16; ++c) t.col[i][c] = (c < 13) ? t.jx[i][c] : t.ju[i][c - 13];
-    return t;
-}
-__device__ constexpr SlotTab SLOT_TAB = make_slot_tab();
-__device__ __forceinline__ constexpr int jx_slot(int i, int j) { return SLOT_TAB.jx[i][j]; }
-__device__ __forceinline__ constexpr int ju_slot(int i, int j) { return SLOT_TAB.ju[i][j]; }
-static_assert(make_slot_tab().jx[12][12] == 103, "slot numbering");
-static_assert(make_slot_tab().ju[5][2] == JAC_SLOTS_NOARM - 1, "slot numbering");
-static_assert(make_slot_tab().jx[5][12] == JAC_SLOTS - 1, "slot numbering");
+constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7 structural non-zeros of a zero-arm model (+ 21 with a tether arm)
 
 // Sink: dense 13x13 / 13x3 row-major, SoA over units (buffers pre-zeroed by the caller).
 struct DenseSink {
@@ -263,8 +241,9 @@ struct SensArgs {
 
 
 // ---- compact slots of the sensitivity tile ------------------------------------------------------------------
-// As SLOT_TAB, but the 12 entries d q_dot / d w = {+-q/2} (kite_model.cuh, Qw) that repeat a value WITH ITS SIGN share a
-// slot (12 -> 7): 106 slots without a tether arm (127 with), so that eight warps' tiles fit one SM's shared memory.
+// Row-major over the structural non-zeros: Jx first, then Ju, then the tether-arm extras.  The 12 entries
+// d q_dot / d w = {+-q/2} (kite_model.cuh, Qw) that repeat a value WITH ITS SIGN share a slot (12 -> 7): 106 slots
+// without a tether arm (127 with), so that eight warps' tiles fit one SM's shared memory.
 struct SensTab { int jx[13][13]; int ju[13][3]; int col[13][16]; };
 constexpr int SENS_SLOTS_NOARM = JAC_SLOTS_NOARM - 5, SENS_SLOTS = JAC_SLOTS - 5;
 constexpr SensTab make_sens_tab() {
