@@ -348,7 +348,7 @@ def test_sens_tma_output_matches_direct_stores(eng, oracle):
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), "TMA and direct-store outputs differ"
 
 
-def test_sens_rollout_single_launch_equals_chained_steps(eng, oracle):
+def test_sens_rollout_single_launch_equals_chained_steps(eng, oracle, okb, params):
     """kite_rk4_sens_rollout walks all (step, group) work items in ONE launch, step k of a group waiting for the state
     its step k - 1 published: the result must be bitwise what N chained single-step calls give, for batches smaller and
     larger than one wave of the persistent grid and for TMA-eligible and odd sizes."""
@@ -362,6 +362,17 @@ def test_sens_rollout_single_launch_equals_chained_steps(eng, oracle):
             assert torch.equal(xn, xs[k]) and torch.equal(P1, Phi[k]) and torch.equal(G1, Gam[k]), "step %d of B=%d" % (k, B)
             xk = xn
         assert bool(torch.isfinite(Phi).all())
+    # the rigid-body model takes the direct-store instantiation of the same kernel
+    rb = okb.Engine(params, okb.RIGID_BODY)
+    B, N = 300, 4
+    x0, u = eng.synth_inputs(B, N)
+    xs, Phi, Gam = rb.sens_rollout(x0, u, h)
+    xk = x0
+    for k in range(N):
+        xn, P1, G1 = rb.sens_step(xk, u[k].contiguous(), h)
+        assert torch.equal(xn, xs[k]) and torch.equal(P1, Phi[k]) and torch.equal(G1, Gam[k]), "rigid step %d" % k
+        xk = xn
+    rb.close()
 
 
 def test_persistent_kernels_are_deterministic(eng, oracle):
