@@ -186,12 +186,14 @@ int kite_colloc_cost(kite_ctx* ctx, long B, long ld, int P, int S, const double*
 /* ---------------------------------------------------------------- EKF -------------------- */
 /* Replaces: KiteEKF::propagate (kiteEKF.cpp:75-98): xn = RK4(x,u,dt); A = I + Jx(x,u) dt; Pn = A P A^T + W.
  *   x_d [13][ld], u_d [3][ld], P_d [169][ld], W_h HOST 13x13 row-major; xn_d, Pn_d like x_d, P_d.
- *   work_d: device scratch of kite_ekf_work_bytes(B) bytes (currently 0: the Jacobian stays in shared memory; may be NULL). */
+ *   work_d: device scratch of kite_ekf_work_bytes(B) bytes (currently 0: the Jacobian stays in shared memory; may be NULL).
+ *   P_d and Pn_d must not alias.  The covariance moves as TMA boxes when P_d / Pn_d have a 16-byte aligned base and
+ *   pitch (even ld) and B is even, through ordinary loads / stores otherwise: same arithmetic either way. */
 size_t kite_ekf_work_bytes(long B);
 int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const double* x_d, const double* u_d,
                            const double* P_d, const double* W_h, double* xn_d, double* Pn_d, void* work_d);
 /* Replaces: the update half of KiteEKF::_estimate (kiteEKF.cpp:115-125) with H = [0 I7]:
- *   z_d [7][ld] measurements, V_h HOST 7x7; x_d, P_d updated in place. */
+ *   z_d [7][ld] measurements, V_h HOST 7x7; x_d, P_d updated in place (one kernel, no staging copy of P). */
 int kite_ekf_update_batch(kite_ctx* ctx, long B, long ld, const double* z_d, const double* V_h, double* x_d, double* P_d);
 
 /* ---------------------------------------------------------------- multi-GPU -------------- */
