@@ -218,12 +218,20 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
 //                           warp (an L2 / HBM round trip in the earlier version: 3.7 GB of write-back per 1 M units) to
 //                           8 units x 4 stages = 27 KB: they stay in the warp's SHARED-memory tile
 //                           [stage][pass][slot][4 units], written conflict free straight from the Jacobian code.
-//   phase B (8 lanes = unit, 4 units per pass, 2 passes): lane l owns tangent columns {2l, 2l+1} of [Phi | Gamma] and
-//                           runs the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in registers
-//                           (E = seed [I | 0; 0 | I]); stage 1 is a pure gather of two Jacobian columns.  Jacobian
-//                           entries are conflict-free broadcast LDS.64 with immediate offsets; [Phi | Gamma] leaves
-//                           straight from registers as full 32 B sectors (4 consecutive units per row).
-//   No TMA, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
+//   phase B (8 consecutive lanes = unit, 4 units per pass, 2 passes): lane l of a unit owns tangent columns {l, l + 8} of
+//                           [Phi | Gamma] and runs the recursion D_i = E + a_i h S_{i-1}, S_i = [Jx_i | Ju_i] D_i in
+//                           registers (E = seed [I | 0; 0 | I]); stage 1 is a pure gather of two Jacobian columns through
+//                           a shared offset table.  Jacobian entries are one-wavefront broadcast LDS.64 with immediate
+//                           offsets.
+//   output:                 [Phi | Gamma] of a round is staged as ONE [169][8 units] and ONE [39][8 units] box in pass 0's
+//                           dead tiles (TMA 64-byte swizzle, per-lane offset table: conflict-free stores) and leaves by
+//                           two TMA tensor stores of 64-byte rows; the tensor map clips the ragged tail.  A direct-store
+//                           instantiation (TMA_OUT = false) serves layouts the TMA cannot address.
+//   No TMA loads, no mbarriers, no ring: producer and consumer are the same warp, ordered by __syncwarp.
+//   Multiple-shooting rollouts (N steps, the state of step k feeding step k + 1) run in the SAME launch: the work items
+//   are (step, group) pairs claimed in step-major order, a warp that claims step k of a group waits (normally not at
+//   all: the item was issued a whole wave earlier) until the group's step k - 1 has published its state.  One launch and
+//   one tail for the whole horizon instead of one per step.
 // ================================================================================================
 struct SensArgs {
     alignas(64) CUtensorMap tmPhi;    // [N][169][B] rows of ld doubles, box [1][169][8 units]  (only read by the TMA-output kernels)
@@ -525,9 +533,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 }
                 if (TMA_OUT) {
                     // [Phi | Gamma] = E + h/6 A staged in the [169][8] / [39][8] boxes of the round (units 4 p .. 4 p + 3 of
-                    // every row; shared-memory stores with immediate offsets) and, after the second pass, written by two
-                    // TMA tensor stores of 64-byte rows: the LSU sees 26 four-wavefront shared stores per pass instead
-                    // of 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by the
+                    // every row; swizzled offsets from the staging table) and, after the second pass, written by two
+                    // TMA tensor stores of 64-byte rows: the LSU sees 26 conflict-free shared stores per pass instead of
+                    // 26 eight-sector global stores with 64-bit address arithmetic; units >= B are clipped by the
                     // tensor map
                     unsigned char* const wb = smem_raw + (size_t)warp * C::SMEM_PER_WARP;
                     unsigned char* const bphi = wb + C::BOX_PHI;
