@@ -419,6 +419,42 @@ def test_persistent_kernels_are_deterministic(eng, oracle):
     assert_close(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), RTOL, what="EKF TMA vs direct")
 
 
+def test_tma_paths_random_shapes(eng, oracle):
+    """Random even (B, ld) shapes around the box / round / group / wave sizes: the TMA paths of the sensitivity step and of
+    the EKF predict against the direct kernels (odd pitch), padding columns untouched, ragged tails clipped."""
+    import ctypes as C
+    rng = np.random.default_rng(2026)
+    W, _ = oracle.ekf_defaults()
+    Wh = np.ascontiguousarray(W)
+    sizes = [2, 6, 8, 30, 34, 62, 66, 254, 258, 1022, 1026, 4094] + [int(2 * rng.integers(1, 20000)) for _ in range(6)]
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for B in sizes:
+        x0, u = eng.synth_inputs(B, 1)
+        P = torch.from_numpy((10 * W).reshape(169, 1)).cuda().expand(169, B).contiguous()
+        P = P * (1.0 + 0.01 * torch.rand(169, B, dtype=torch.float64, device="cuda"))
+        res = []
+        for ld in (B + 2 * int(rng.integers(0, 5)), B + 1 + 2 * int(rng.integers(0, 5))):       # even pitch: TMA, odd: direct
+            def pad(t):
+                o = torch.zeros(t.shape[0], ld, dtype=torch.float64, device="cuda"); o[:, :B] = t; return o
+            xd, ud, Pd = pad(x0), pad(u[0]), pad(P)
+            mk = lambda r: torch.full((r, ld), -7.0, dtype=torch.float64, device="cuda")
+            xn, Phi, Gam, xe, Pn = mk(13), mk(169), mk(39), mk(13), mk(169)
+            w = eng.workspace(eng.L.kite_rk4_sens_work_bytes(B))
+            eng._use_torch_stream()
+            eng._ck(eng.L.kite_rk4_sens_step(eng.ctx, B, ld, 0.02, p(xd), p(ud), p(xn), p(Phi), p(Gam), p(w)))
+            eng._ck(eng.L.kite_ekf_predict_batch(eng.ctx, B, ld, 0.0084, p(xd), p(ud), p(Pd), Wh.ctypes.data_as(C.c_void_p), p(xe), p(Pn), None))
+            torch.cuda.synchronize()
+            for t in (xn, Phi, Gam, xe, Pn):
+                if ld > B:
+                    assert float((t[:, B:] + 7.0).abs().max()) == 0.0, "padding written (B=%d ld=%d)" % (B, ld)
+            res.append([t[:, :B].clone() for t in (xn, Phi, Gam, xe, Pn)])
+        for a_, b_, name in zip(res[0], res[1], ("xn", "Phi", "Gamma", "ekf xn", "ekf Pn")):
+            if name == "ekf Pn":
+                assert_close(a_.cpu().numpy(), b_.cpu().numpy(), RTOL, what="%s B=%d" % (name, B))
+            else:
+                assert torch.equal(a_, b_), "%s differs between the TMA and the direct path (B=%d)" % (name, B)
+
+
 def test_sens_linearity_property(eng, oracle):
     """Size-independent property: Phi dx + Gamma du predicts the perturbed step to second order."""
     B, h = 2048, 0.02
