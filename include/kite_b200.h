@@ -90,8 +90,11 @@ long long kite_launch_count(const kite_ctx* ctx);
 
 /* Device-memory helpers so that an FFI host (C++, cgo, JNI, ctypes) needs no CUDA runtime binding of its own.
  * Copies are issued on the context's stream and complete before returning. */
-int kite_device_malloc(void** ptr_out, size_t bytes);
+int kite_device_malloc(void** ptr_out, size_t bytes);   /* on the CURRENT device of the calling thread */
 int kite_device_free(void* ptr);
+/* Same, on the context's device (use these when a process owns contexts on several GPUs). */
+int kite_ctx_malloc(kite_ctx* ctx, void** ptr_out, size_t bytes);
+int kite_ctx_free(kite_ctx* ctx, void* ptr);
 int kite_copy_h2d(kite_ctx* ctx, void* dst_d, const void* src_h, size_t bytes);
 int kite_copy_d2h(kite_ctx* ctx, void* dst_h, const void* src_d, size_t bytes);
 

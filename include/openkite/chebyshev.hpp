@@ -44,9 +44,9 @@ public:
             for (int i = 0; i < 15; ++i) sx[i] = Sx.size2() > 1 ? Sx(i, i) : Sx[i];
             for (int i = 0; i < 4; ++i) su[i] = Su.size2() > 1 ? Su(i, i) : Su[i];
             const size_t nd = (size_t)NODES * (19 + 15 + 225 + 60) + 1;
-            if (kite_device_malloc((void**)&buf, sizeof(double) * nd) != 0) throw std::runtime_error("Collocated: device allocation failed");
+            if (kite_ctx_malloc(Ctx->ctx, (void**)&buf, sizeof(double) * nd) != 0) throw std::runtime_error("Collocated: device allocation failed");
         }
-        ~Collocated() { if (buf) kite_device_free(buf); }
+        ~Collocated() { if (buf) kite_ctx_free(Ctx->ctx, buf); }
         Collocated(const Collocated&) = delete;
 
         /** constraint residual G (NODES*15), as DynamicConstraints / nlp_g (kiteNMPF.cpp:151) */
@@ -106,9 +106,9 @@ public:
             : Ctx(ctx), tau_(tau), cost_(c) {
             for (int i = 0; i <= PolyOrder; ++i) qw_[i] = qw.size1() > 1 ? qw[i] : qw(0, i);
             for (int i = 0; i < 15; ++i) sx[i] = Sx.size2() > 1 ? Sx(i, i) : Sx[i];
-            if (kite_device_malloc((void**)&buf, sizeof(double) * ((size_t)NODES * 38 + 1)) != 0) throw std::runtime_error("CollocatedCost: device allocation failed");
+            if (kite_ctx_malloc(Ctx->ctx, (void**)&buf, sizeof(double) * ((size_t)NODES * 38 + 1)) != 0) throw std::runtime_error("CollocatedCost: device allocation failed");
         }
-        ~CollocatedCost() { if (buf) kite_device_free(buf); }
+        ~CollocatedCost() { if (buf) kite_ctx_free(Ctx->ctx, buf); }
         CollocatedCost(const CollocatedCost&) = delete;
         /** performance_idx(z), as PerformanceIndex / nlp_f (kiteNMPF.cpp:143,152) */
         double operator()(const DM& z) { DM g; return eval(z, g, false); }

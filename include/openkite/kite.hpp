@@ -103,9 +103,9 @@ public:
     KiteContext(const kite_params& p, int model_kind, int device = 0) : params(p), kind(model_kind) {
         int rc = kite_create(&ctx, &p, model_kind, device);
         if (rc != KITE_OK) throw std::runtime_error("kite_create failed (status " + std::to_string(rc) + "): a CUDA device is required, there is no CPU fallback");
-        if (kite_device_malloc((void**)&stage, sizeof(double) * STAGE_DOUBLES) != 0) throw std::runtime_error("device staging allocation failed");
+        if (kite_ctx_malloc(ctx, (void**)&stage, sizeof(double) * STAGE_DOUBLES) != 0) throw std::runtime_error("device staging allocation failed");
     }
-    ~KiteContext() { if (stage) kite_device_free(stage); if (ctx) kite_destroy(ctx); }
+    ~KiteContext() { if (stage) kite_ctx_free(ctx, stage); if (ctx) kite_destroy(ctx); }
     KiteContext(const KiteContext&) = delete;
     KiteContext& operator=(const KiteContext&) = delete;
 

@@ -60,11 +60,12 @@ public:
 
     /** x+ = RK4(x,u,dt);  A = I + Jx(x,u) dt (at the pre-step state);  P+ = A P A^T + W   (kiteEKF.cpp:75-98) */
     void propagate(const double& _dt) {
-        if (m_Integrator.name().find("RK4") == std::string::npos) {
-            // kiteEKF.cpp:83-90: a CVODES-named integrator is outside the GPU path; anything else is unknown
-            std::cout << "WARNING: Unknown intergrator! \n";
-            return;
-        }
+        const bool rk4 = m_Integrator.name().find("RK4") != std::string::npos;
+        if (!rk4 && m_Integrator.name().find("CVODES") != std::string::npos)
+            // kiteEKF.cpp:83-88: the CVODES branch integrates with SUNDIALS, which is outside the GPU path;
+            // failing loudly beats silently skipping the covariance propagation
+            throw std::runtime_error("KiteEKF::propagate: a CVODES integrator is not supported by the GPU engine (use RK4)");
+        if (!rk4) std::cout << "WARNING: Unknown intergrator! \n";          // kiteEKF.cpp:89-90, then falls through like the reference
         if (State_Est.numel() != 13) throw std::invalid_argument("KiteEKF::propagate: set the estimation first");
         DM u = Control.is_empty() ? DM::zeros(3) : Control;
         double* s = Ctx->stage;
@@ -77,7 +78,10 @@ public:
                                           Wr.data(), s + 208, s + 224, s + 400), "kite_ekf_predict_batch");
         DM x(13, 1); Ctx->d2h(x.ptr(), s + 208, 13);
         Ctx->d2h(P.data(), s + 224, 169);
-        State_Est = x; Cov_Est = DM::from_row_major(P.data(), 13, 13);
+        // the covariance is propagated whichever integrator branch was taken (kiteEKF.cpp:92-97); with an unknown
+        // integrator the reference assigns a default-constructed (empty) state
+        State_Est = rk4 ? x : DM();
+        Cov_Est = DM::from_row_major(P.data(), 13, 13);
     }
 
     /** Batched predict for an ensemble of B filters (device SoA pointers, include/kite_b200.h). */

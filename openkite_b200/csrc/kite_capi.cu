@@ -150,6 +150,18 @@ int kite_device_malloc(void** ptr_out, size_t bytes) {
     return cudaMalloc(ptr_out, bytes) == cudaSuccess ? KITE_OK : KITE_ERR_CUDA;
 }
 int kite_device_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? KITE_OK : KITE_ERR_CUDA; }
+int kite_ctx_malloc(kite_ctx* ctx, void** ptr_out, size_t bytes) {
+    if (!ctx || !ptr_out) return fail(ctx, KITE_ERR_ARG, "kite_ctx_malloc: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(ptr_out, bytes));
+    return KITE_OK;
+}
+int kite_ctx_free(kite_ctx* ctx, void* ptr) {
+    if (!ctx) return KITE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(ptr));
+    return KITE_OK;
+}
 int kite_copy_h2d(kite_ctx* ctx, void* dst_d, const void* src_h, size_t bytes) {
     if (!ctx || !dst_d || !src_h) return fail(ctx, KITE_ERR_ARG, "kite_copy_h2d: bad argument");
     CK(cudaSetDevice(ctx->device));
@@ -183,8 +195,10 @@ static int point_eval(kite_ctx* ctx, long B, long ld, const double* x, const dou
     if (rigid && p) return fail(ctx, KITE_ERR_STATE, "point_eval: rigid body has no aero parameters");
     CK(cudaSetDevice(ctx->device));
     if (jac) {
-        if (Jx) CK(cudaMemsetAsync(Jx, 0, sizeof(double) * 169 * (size_t)ld, ctx->stream));
-        if (Ju) CK(cudaMemsetAsync(Ju, 0, sizeof(double) * 39 * (size_t)ld, ctx->stream));
+        // zero only the B valid columns of every row: with ld > B the padding (a neighbouring sub-batch of a larger
+        // [rows][ld] allocation) must stay untouched
+        if (Jx) CK(cudaMemset2DAsync(Jx, sizeof(double) * (size_t)ld, 0, sizeof(double) * (size_t)B, 169, ctx->stream));
+        if (Ju) CK(cudaMemset2DAsync(Ju, sizeof(double) * (size_t)ld, 0, sizeof(double) * (size_t)B, 39, ctx->stream));
     }
     PointArgs a{ctx->K, B, ld, x, u, p, f, Jx, Ju};
     launch_point_eval(a, rigid, p != nullptr, jac, ctx->stream);
@@ -236,6 +250,8 @@ int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, doubl
 }
 
 // Host-pointer rollout: chunk over trajectories, double-buffered H2D / compute / D2H on three streams.
+static int rollout_host_pipeline(kite_ctx* ctx, long B, long N, double h, const double* x0_h, const double* u_h, int u_mode,
+                                 const double* p_h, double* xf_h, const double* y_h, double* cost_h, int32_t* status_h);
 int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double* x0_h, const double* u_h, int u_mode,
                           const double* p_h, double* xf_h, const double* y_h, double* cost_h, int32_t* status_h) {
     if (ctx && B == 0) return KITE_OK;
@@ -244,8 +260,23 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     if (!u_h && !rigid) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: u_h is null");
     if ((y_h != nullptr) != (cost_h != nullptr)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout_host: y/cost go together");
-    if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
+    const int rc = rollout_host_pipeline(ctx, B, N, h, x0_h, u_h, u_mode, p_h, xf_h, y_h, cost_h, status_h);
+    if (rc != KITE_OK) {
+        // an error in the middle of the pipeline leaves copies on the caller's host buffers and kernels in flight on three
+        // streams: drain them before handing the buffers back (the first error message is kept)
+        const std::string first = ctx->err;
+        if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+        cudaGetLastError();
+        ctx->err = first;
+    }
+    return rc;
+}
+static int rollout_host_pipeline(kite_ctx* ctx, long B, long N, double h, const double* x0_h, const double* u_h, int u_mode,
+                                 const double* p_h, double* xf_h, const double* y_h, double* cost_h, int32_t* status_h) {
+    const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
     if (!ctx->h2d_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));

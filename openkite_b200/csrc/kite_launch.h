@@ -9,7 +9,8 @@ void launch_rollout_23(const RolloutArgs& a, int umode, bool rigid, bool percoef
 void launch_synth_inputs(const SynthArgs& a, cudaStream_t s);
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s);
 bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows, long N);   // false: layout not TMA-eligible
-long sens_fused_max_warps();   // warps of the persistent fused kernel on the current device (scratch sizing)
+int current_device_sms();      // SM count of the CURRENT device (0 if none)
+long sens_fused_max_warps();   // upper bound of the resident warps of the persistent fused kernel over all visible devices (scratch sizing)
 void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, cudaStream_t s);
 size_t ekf_predict_scratch_bytes();   // pre-step state lines of the resident warps of the TMA kernel (independent of B)
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);

@@ -4,13 +4,9 @@
 namespace kite {
 template <bool ARM, bool RIGID>
 static void go_predict(const EkfArgs& a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_ekf_predict<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EfCfg<ARM>::SMEM);
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // per-device attribute, set on every launch (contexts may live on several devices of one process)
+    cudaFuncSetAttribute(k_ekf_predict<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EfCfg<ARM>::SMEM);
+    const int sms = current_device_sms();
     const long ngroups = (a.B + 31) / 32;
     const long want = (ngroups + EfCfg<ARM>::WARPS - 1) / EfCfg<ARM>::WARPS;
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
@@ -18,22 +14,16 @@ static void go_predict(const EkfArgs& a, cudaStream_t s) {
 }
 template <bool ARM, bool RIGID>
 static void go_predict_tma(const EkfTmaArgs& a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_ekf_predict_tma<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EtCfg<ARM>::SMEM);
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    cudaFuncSetAttribute(k_ekf_predict_tma<ARM, RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EtCfg<ARM>::SMEM);
+    const int sms = current_device_sms();
     const long ngroups = (a.e.B + 31) / 32;
     const long want = (ngroups + EtCfg<ARM>::WARPS - 1) / EtCfg<ARM>::WARPS;
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
     k_ekf_predict_tma<ARM, RIGID><<<grid, EtCfg<ARM>::WARPS * 32, EtCfg<ARM>::SMEM, s>>>(a);
 }
 size_t ekf_predict_scratch_bytes() {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-        sms = 256;
+    int sms = current_device_sms();        // the scratch is a per-context buffer, sized for the context's (current) device
+    if (sms <= 0) sms = 256;
     return sizeof(double) * (size_t)ET_SCRATCH_PER_WARP * 8 * (size_t)sms;
 }
 void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, cudaStream_t s) {
@@ -55,8 +45,7 @@ void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, c
 }
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s) {
     constexpr int smem = (int)sizeof(double) * (91 + 13) * EKFU_BLOCK;
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_ekf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    cudaFuncSetAttribute(k_ekf_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k_ekf_update<0><<<blocks_for(a.B, EKFU_BLOCK), EKFU_BLOCK, smem, s>>>(a);
 }
 }  // namespace kite

@@ -4,29 +4,35 @@
 namespace kite {
 template <bool ARM, bool RIGID, bool TMA_OUT>
 static void go_fused(const SensArgs& a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_sens_fused<ARM, RIGID, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
-        configured = true;
-    }
+    // the opt-in is a per-device function attribute and a host may own contexts on several devices: set it on every
+    // launch (a few hundred nanoseconds) instead of caching a per-process flag
+    cudaFuncSetAttribute(k_sens_fused<ARM, RIGID, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SfCfg<ARM>::SMEM);
     // one warp per group at most: the steps of a group depend on each other, and the scratch (kite_rk4_sens_work_bytes)
     // holds one line per resident warp of a grid sized by the GROUP count
     const long ngroups = (a.B + 31) / 32;
     constexpr int W = SfCfg<ARM>::WARPS;
     const long want = (ngroups + W - 1) / W;
-    const long sms = sens_fused_max_warps() / SF_WARPS;
+    const long sms = current_device_sms();
     const unsigned grid = (unsigned)(want < sms ? want : sms);          // persistent: one CTA per SM
     k_sens_fused<ARM, RIGID, TMA_OUT><<<grid, W * 32, SfCfg<ARM>::SMEM, s>>>(a);
 }
+int current_device_sms() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        return 0;
+    return sms;
+}
+// Upper bound of the resident warps of the persistent kernel on ANY visible device (the scratch-size query has no
+// context argument, and a host may own contexts on several devices).
 long sens_fused_max_warps() {
-    static long warps = 0;
-    if (!warps) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            return 256L * SF_WARPS;                                     // no device visible: a safe upper bound for sizing
-        warps = (long)sms * SF_WARPS;
+    int ndev = 0, best = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = 0;
+    for (int d = 0; d < ndev; ++d) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && sms > best) best = sms;
     }
-    return warps;
+    if (best <= 0) best = 256;                                          // no device visible: a safe upper bound for sizing
+    return (long)best * SF_WARPS;
 }
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -289,6 +289,25 @@ def test_padded_leading_dimension(eng, okb, oracle):
     xf = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda")
     eng._ck(eng.L.kite_rk4_rollout(eng.ctx, B, ld, 25, 1e-3, p(xd), p(ud), okb.U_CONST, None, p(xf), None, 0, None, None, None, 0))
     assert_close(aos(xf[:, :B]), oracle.rollout(x, u, 25, 1e-3), RTOL, what="rollout ld>B")
+    # pointwise Jacobians with ld > B: the structural zeros are cleared for the B valid columns only, the padding of every
+    # row (a neighbouring sub-batch of a larger [rows][ld] allocation) keeps its sentinel
+    Jx = torch.full((169, ld), -7.0, dtype=torch.float64, device="cuda"); Ju = torch.full((39, ld), -7.0, dtype=torch.float64, device="cuda")
+    fo = torch.full((13, ld), -7.0, dtype=torch.float64, device="cuda")
+    eng._ck(eng.L.kite_jac_batch(eng.ctx, B, ld, p(xd), p(ud), None, p(Jx), p(Ju)))
+    eng._ck(eng.L.kite_rhs_batch(eng.ctx, B, ld, p(xd), p(ud), None, p(fo)))
+    rJx, rJu = oracle.jac(x, u)
+    assert_close(aos(Jx[:, :B], 13, 13), rJx, RTOL, what="Jx ld>B"); assert_close(aos(Ju[:, :B], 13, 3), rJu, RTOL, what="Ju ld>B")
+    assert_close(aos(fo[:, :B]), oracle.rhs(x, u), RTOL, what="f ld>B")
+    assert float((Jx[:, B:] + 7.0).abs().max()) == 0.0 and float((Ju[:, B:] + 7.0).abs().max()) == 0.0
+    assert float((fo[:, B:] + 7.0).abs().max()) == 0.0
+    # a sub-batch at a column offset inside the same allocation: neighbours on both sides stay untouched
+    off, B2 = 40, 30
+    Jx.fill_(-7.0)
+    po = lambda t: C.c_void_p(t.data_ptr() + 8 * off)
+    eng._ck(eng.L.kite_jac_batch(eng.ctx, B2, ld, po(xd), po(ud), None, po(Jx), None))
+    torch.cuda.synchronize()
+    assert_close(aos(Jx[:, off:off + B2], 13, 13), rJx[off:off + B2], RTOL, what="Jx sub-batch")
+    assert float((Jx[:, :off] + 7.0).abs().max()) == 0.0 and float((Jx[:, off + B2:] + 7.0).abs().max()) == 0.0
 
 
 def test_sens_scratch_stays_inside_work_bytes(eng, oracle):
