@@ -132,6 +132,12 @@ int kite_rk4_rollout_host(kite_ctx* ctx, long B, long N, double h, const double*
  * [index0, index0+B).  Workload definition, not reference behaviour. */
 int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, double* x0_d, double* u_d);
 
+/* Fill p_d [21][ld] with the parameter samples of the identification sweep for global indices [index0, index0+B)
+ * (SURVEY.md 8d config 5): the reference coefficients (pref_h[21] HOST, order of kite.cpp:571-572; NULL = the context's
+ * own) perturbed uniformly inside the bounds of kite_identification_test.cpp:127-148, keyed on the global index so that
+ * the samples are identical under any sharding.  Workload definition, not reference behaviour. */
+int kite_synth_id_params(kite_ctx* ctx, long B, long ld, long index0, const double* pref_h, double* p_d);
+
 /* ---------------------------------------------------------------- sensitivities ---------- */
 /* One RK4 step with forward-mode sensitivities for B independent shooting intervals:
  *   xn = RK4(x,u,h), Phi = d xn/d x (13x13), Gamma = d xn/d u (13x3).

@@ -249,6 +249,21 @@ int kite_synth_inputs(kite_ctx* ctx, long B, long ld, long N, long index0, doubl
     return KITE_OK;
 }
 
+int kite_synth_id_params(kite_ctx* ctx, long B, long ld, long index0, const double* pref_h, double* p_d) {
+    if (!ctx || B < 0 || ld < B || !p_d) return fail(ctx, KITE_ERR_ARG, "kite_synth_id_params: bad argument");
+    if (B == 0) return KITE_OK;
+    CK(cudaSetDevice(ctx->device));
+    const kite_params& P = ctx->params;
+    const double nominal[21] = {P.CL0, P.CLa_total, P.CD0_total, P.CYb, P.Cm0, P.Cma, P.Cnb, P.Clb, P.CLq, P.Cmq, P.CYr,
+                                P.Cnr, P.Clr, P.CYp, P.Clp, P.Cnp, P.CLde, P.CYdr, P.Cmde, P.Cndr, P.Cldr};
+    SynthParamArgs a{};
+    a.B = B; a.ld = ld; a.index0 = index0; a.p = p_d;
+    for (int c = 0; c < 21; ++c) a.ref[c] = pref_h ? pref_h[c] : nominal[c];
+    launch_synth_id_params(a, ctx->stream);
+    LAUNCH_CHECK("k_synth_id_params");
+    return KITE_OK;
+}
+
 // Host-pointer rollout: chunk over trajectories, double-buffered H2D / compute / D2H on three streams.
 static int rollout_host_pipeline(kite_ctx* ctx, long B, long N, double h, const double* x0_h, const double* u_h, int u_mode,
                                  const double* p_h, double* xf_h, const double* y_h, double* cost_h, int32_t* status_h);

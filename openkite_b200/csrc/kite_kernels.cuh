@@ -206,6 +206,16 @@ __global__ void __launch_bounds__(256) k_synth_inputs(const __grid_constant__ Sy
     }
 }
 
+// Parameter samples of the identification sweep (p [21][ld]) for global indices [index0, index0 + B).
+struct SynthParamArgs { long B, ld, index0; double ref[21]; double* p; };
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256) k_synth_id_params(const __grid_constant__ SynthParamArgs a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.B) return;
+#pragma unroll
+    for (int c = 0; c < 21; ++c) a.p[(long)c * a.ld + i] = synth_id_param((uint64_t)(a.index0 + i), c, a.ref[c]);
+}
+
 // ================================================================================================
 // RK4 step sensitivities: one persistent kernel, every warp independent (no CTA barrier anywhere), the stage Jacobians
 // never leave the SM.  A warp owns groups of 32 units, claimed from a global counter.  Per group:

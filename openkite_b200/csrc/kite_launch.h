@@ -7,6 +7,7 @@ void launch_point_eval(const PointArgs& a, bool rigid, bool percoef, bool jac, c
 void launch_rollout_01(const RolloutArgs& a, int umode, bool rigid, bool percoef, cudaStream_t s);
 void launch_rollout_23(const RolloutArgs& a, int umode, bool rigid, bool percoef, cudaStream_t s);
 void launch_synth_inputs(const SynthArgs& a, cudaStream_t s);
+void launch_synth_id_params(const SynthParamArgs& a, cudaStream_t s);
 void launch_sens_fused(const SensArgs& a, bool rigid, bool arm, bool tma_out, cudaStream_t s);
 bool sens_make_tensor_map(CUtensorMap* tm, double* base, long B, long ld, int rows, long N);   // false: layout not TMA-eligible
 int current_device_sms();      // SM count of the CURRENT device (0 if none)

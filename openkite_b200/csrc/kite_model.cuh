@@ -545,4 +545,21 @@ __device__ __forceinline__ void synth_x0(uint64_t traj, double (&x0)[13]) {
     for (int c = 9; c < 13; ++c) x0[c] = x0[c] / nrm;
 }
 
+// Identification sweep: parameter sample `traj` = reference coefficients perturbed uniformly inside
+// the bounds of kite_identification_test.cpp:127-148 (fractions of |ref|), keyed on the GLOBAL sample index.
+#define KITE_ID_BOUNDS_LO {-0.1, -0.05, -0.1, -0.5, -0.5, -0.1, -0.5, -0.5, -0.2, -0.3, -0.3, -0.5, -0.5, -0.5, -0.5, -0.3, -0.5, -0.5, -0.5, -0.5, -0.5}
+#define KITE_ID_BOUNDS_HI {0.1, 0.1, 0.25, 0.5, 0.5, 0.30, 0.5, 0.5, 0.2, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 1.0, 0.5, 0.5, 0.5, 0.5, 0.5}
+__host__ __device__ inline double synth_id_param(uint64_t traj, int c, double ref) {
+    const double lo[21] = KITE_ID_BOUNDS_LO, hi[21] = KITE_ID_BOUNDS_HI;
+    const double t = counter_uniform(KITE_SYNTH_SEED, traj, 0xFFFFFEULL, (uint64_t)c);
+#ifdef __CUDA_ARCH__
+    const double frac = __dadd_rn(lo[c], __dmul_rn(__dadd_rn(hi[c], -lo[c]), t));
+    return __dadd_rn(ref, __dmul_rn(fabs(ref), frac));
+#else
+    const double w = hi[c] - lo[c];
+    const double frac = lo[c] + w * t;
+    return ref + fabs(ref) * frac;
+#endif
+}
+
 }  // namespace kite

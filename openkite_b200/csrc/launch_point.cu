@@ -18,6 +18,9 @@ void launch_synth_inputs(const SynthArgs& a, cudaStream_t s) {
     dim3 grid(blocks_for(a.B, 256), (unsigned)gy), block(256);
     k_synth_inputs<0><<<grid, block, 0, s>>>(a);
 }
+void launch_synth_id_params(const SynthParamArgs& a, cudaStream_t s) {
+    k_synth_id_params<0><<<blocks_for(a.B, 256), 256, 0, s>>>(a);
+}
 void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s) {
     k_math_selftest<0><<<blocks_for(n, 256), 256, 0, s>>>(x, out, n, which);
 }

@@ -97,6 +97,9 @@ def load_library():
     L.kite_rk4_rollout.argtypes = [vp, lg, lg, lg, db, dp, dp, ip, dp, dp, dp, lg, dp, dp, dp, lg]
     L.kite_rk4_rollout_host.argtypes = [vp, lg, lg, db, dp, dp, ip, dp, dp, dp, dp, dp]
     L.kite_synth_inputs.argtypes = [vp, lg, lg, lg, lg, dp, dp]
+    L.kite_synth_id_params.argtypes = [vp, lg, lg, lg, dp, dp]
+    L.kite_ctx_malloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    L.kite_ctx_free.argtypes = [vp, vp]
     L.kite_rk4_sens_work_bytes.argtypes = [lg]; L.kite_rk4_sens_work_bytes.restype = C.c_size_t
     L.kite_rk4_sens_step.argtypes = [vp, lg, lg, db, dp, dp, dp, dp, dp, dp]
     L.kite_rk4_sens_rollout.argtypes = [vp, lg, lg, lg, db, dp, dp, dp, dp, dp, dp]
@@ -200,7 +203,7 @@ class Engine:
 
     # ---- rollouts ------------------------------------------------------------------------------
     def rollout(self, x0, u, N, h, u_mode=U_CONST, p=None, save_every=0, y=None, want_status=True, index0=0, B=None,
-                out=None):
+                out=None, cost_out=None, status_out=None):
         """x0 [13,B]; u per u_mode ([3,B] | [N,3,B] | [N,3]); returns dict(xf, traj, cost, status)."""
         self._use_torch_stream()
         if u_mode == U_SYNTH:
@@ -209,8 +212,8 @@ class Engine:
             B = x0.shape[1]
         xf = out if out is not None else self.empty(13, B)
         traj = self.empty(N // save_every, 13, B) if save_every else None
-        cost = self.empty(B) if y is not None else None
-        status = torch.empty(B, dtype=torch.int32, device=self.device) if want_status else None
+        cost = (cost_out if cost_out is not None else self.empty(B)) if y is not None else None
+        status = status_out if status_out is not None else (torch.empty(B, dtype=torch.int32, device=self.device) if want_status else None)
         self._ck(self.L.kite_rk4_rollout(self.ctx, B, B, N, h, _ptr(x0), _ptr(u), u_mode, _ptr(p), _ptr(xf), _ptr(traj),
                                          save_every, _ptr(y), _ptr(cost), _ptr(status), index0))
         return dict(xf=xf, traj=traj, cost=cost, status=status)
@@ -229,6 +232,38 @@ class Engine:
         u = self.empty(max(N, 1), 3, B) if want_u else None
         self._ck(self.L.kite_synth_inputs(self.ctx, B, B, N if want_u else 0, index0, _ptr(x0), _ptr(u)))
         return x0, u
+
+    def synth_id_params(self, B, index0=0, ref=None):
+        """Parameter samples [21, B] of the identification sweep for global indices [index0, index0 + B)."""
+        self._use_torch_stream()
+        p = self.empty(21, B)
+        ra, rp = _hostarr(ref) if ref is not None else (None, None)
+        self._ck(self.L.kite_synth_id_params(self.ctx, B, B, index0, rp, _ptr(p)))
+        return p
+
+    # ---- multi-GPU: the library's own NCCL path (kite_comm_* / kite_allgather) ------------------
+    def comm_init(self, world, rank):
+        """Bootstrap the library communicator: rank 0 draws the NCCL id, torch.distributed (already initialised by the
+        caller: plumbing) carries it to the other ranks."""
+        import torch.distributed as dist
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            self._ck(self.L.kite_comm_unique_id(idbuf))
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, 0)
+        idbuf = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
+        self._ck(self.L.kite_comm_init(self.ctx, world, rank, idbuf))
+        self.world = world
+
+    def allgather(self, send, recv):
+        """recv[world * n] <- concatenation over ranks of send[n] (FP64), on the current torch stream."""
+        self._use_torch_stream()
+        assert send.dtype == torch.float64 and recv.dtype == torch.float64 and send.is_contiguous() and recv.is_contiguous()
+        self._ck(self.L.kite_allgather(self.ctx, _ptr(send), _ptr(recv), send.numel()))
+        return recv
+
+    def comm_destroy(self):
+        self._ck(self.L.kite_comm_destroy(self.ctx))
 
     # ---- sensitivities -------------------------------------------------------------------------
     def sens_step(self, x, u, h, out=None):

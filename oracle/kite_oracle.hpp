@@ -591,30 +591,34 @@ inline void ekf_predict(const Params& Pm, ModelKind kind, const double x[13], co
         for (int j = 0; j < 13; ++j) { double a = 0; for (int k = 0; k < 13; ++k) a += AP[i * 13 + k] * A[j * 13 + k]; Pn[i * 13 + j] = a + W[i * 13 + j]; }   // :94
 }
 // Update with H = [0_{7x6} I_7] (kiteEKF.cpp:115-125); in-place on x (13) and P (13x13).
-inline void ekf_update(const double z[7], const double V[49], double x[13], double Pc[169]) {
-    double y[7], Smat[49], Sinv[49], K[13 * 7];
-    for (int i = 0; i < 7; ++i) y[i] = z[i] - x[6 + i];
-    for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) Smat[i * 7 + j] = Pc[(6 + i) * 13 + (6 + j)] + V[i * 7 + j];
+// Templated on the scalar so that the tests can measure the update's own conditioning (T = long double against T = double:
+// the 7x7 innovation covariance is inverted, and the covariance update P - K H P cancels).
+template <class T>
+inline void ekf_update_t(const double z[7], const double V[49], double x[13], double Pc[169]) {
+    T y[7], Smat[49], Sinv[49], K[13 * 7];
+    for (int i = 0; i < 7; ++i) y[i] = T(z[i]) - T(x[6 + i]);
+    for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) Smat[i * 7 + j] = T(Pc[(6 + i) * 13 + (6 + j)]) + T(V[i * 7 + j]);
     // dense inverse by Gauss-Jordan with partial pivoting (DM::solve(S, eye(7)))
-    double aug[7][14];
-    for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) { aug[i][j] = Smat[i * 7 + j]; aug[i][7 + j] = (i == j); }
+    T aug[7][14];
+    for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) { aug[i][j] = Smat[i * 7 + j]; aug[i][7 + j] = T(i == j ? 1.0 : 0.0); }
     for (int c = 0; c < 7; ++c) {
         int piv = c; for (int i = c + 1; i < 7; ++i) if (std::fabs(aug[i][c]) > std::fabs(aug[piv][c])) piv = i;
-        if (piv != c) for (int j = 0; j < 14; ++j) { double t = aug[c][j]; aug[c][j] = aug[piv][j]; aug[piv][j] = t; }
-        double d = aug[c][c]; for (int j = 0; j < 14; ++j) aug[c][j] /= d;
-        for (int i = 0; i < 7; ++i) if (i != c) { double m = aug[i][c]; for (int j = 0; j < 14; ++j) aug[i][j] -= m * aug[c][j]; }
+        if (piv != c) for (int j = 0; j < 14; ++j) { T t = aug[c][j]; aug[c][j] = aug[piv][j]; aug[piv][j] = t; }
+        T d = aug[c][c]; for (int j = 0; j < 14; ++j) aug[c][j] /= d;
+        for (int i = 0; i < 7; ++i) if (i != c) { T m = aug[i][c]; for (int j = 0; j < 14; ++j) aug[i][j] -= m * aug[c][j]; }
     }
     for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) Sinv[i * 7 + j] = aug[i][7 + j];
-    for (int i = 0; i < 13; ++i) for (int j = 0; j < 7; ++j) { double a = 0; for (int k = 0; k < 7; ++k) a += Pc[i * 13 + (6 + k)] * Sinv[k * 7 + j]; K[i * 7 + j] = a; }
-    double xo[13], Po[169];
-    for (int i = 0; i < 13; ++i) { double a = 0; for (int k = 0; k < 7; ++k) a += K[i * 7 + k] * y[k]; xo[i] = x[i] + a; }
+    for (int i = 0; i < 13; ++i) for (int j = 0; j < 7; ++j) { T a = 0; for (int k = 0; k < 7; ++k) a += T(Pc[i * 13 + (6 + k)]) * Sinv[k * 7 + j]; K[i * 7 + j] = a; }
+    T xo[13], Po[169];
+    for (int i = 0; i < 13; ++i) { T a = 0; for (int k = 0; k < 7; ++k) a += K[i * 7 + k] * y[k]; xo[i] = T(x[i]) + a; }
     for (int i = 0; i < 13; ++i) for (int j = 0; j < 13; ++j) {
-        double a = 0; for (int k = 0; k < 7; ++k) a += K[i * 7 + k] * Pc[(6 + k) * 13 + j];   // (K H) P
-        Po[i * 13 + j] = Pc[i * 13 + j] - a;
+        T a = 0; for (int k = 0; k < 7; ++k) a += K[i * 7 + k] * T(Pc[(6 + k) * 13 + j]);   // (K H) P
+        Po[i * 13 + j] = T(Pc[i * 13 + j]) - a;
     }
-    for (int i = 0; i < 13; ++i) x[i] = xo[i];
-    for (int i = 0; i < 169; ++i) Pc[i] = Po[i];
+    for (int i = 0; i < 13; ++i) x[i] = (double)xo[i];
+    for (int i = 0; i < 169; ++i) Pc[i] = (double)Po[i];
 }
+inline void ekf_update(const double z[7], const double V[49], double x[13], double Pc[169]) { ekf_update_t<double>(z, V, x, Pc); }
 
 // ------------------------------------------------------------------------------------
 // Synthetic-input generator shared by the CPU baseline, the tests and the GPU engine's
@@ -648,6 +652,19 @@ inline void synth_control(uint64_t traj, uint64_t step, double u[3]) {
     u[0] = 0.3 * counter_uniform(SYNTH_SEED, traj, step, 0);
     u[1] = amax * (2.0 * counter_uniform(SYNTH_SEED, traj, step, 1) - 1.0);
     u[2] = amax * (2.0 * counter_uniform(SYNTH_SEED, traj, step, 2) - 1.0);
+}
+
+// Identification-sweep parameter sample (config 5): reference coefficients perturbed uniformly inside the bounds of
+// kite_identification_test.cpp:127-148 (fractions of |ref|), channel = coefficient index, step field = 0xFFFFFE.
+static const double ID_BOUNDS_LO[21] = {-0.1, -0.05, -0.1, -0.5, -0.5, -0.1, -0.5, -0.5, -0.2, -0.3, -0.3, -0.5, -0.5, -0.5, -0.5, -0.3, -0.5, -0.5, -0.5, -0.5, -0.5};
+static const double ID_BOUNDS_HI[21] = {0.1, 0.1, 0.25, 0.5, 0.5, 0.30, 0.5, 0.5, 0.2, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 1.0, 0.5, 0.5, 0.5, 0.5, 0.5};
+inline void synth_id_params(uint64_t traj, const double ref[21], double p[21]) {
+    for (int c = 0; c < 21; ++c) {
+        const double t = counter_uniform(SYNTH_SEED, traj, 0xFFFFFEULL, (uint64_t)c);
+        const double w = ID_BOUNDS_HI[c] - ID_BOUNDS_LO[c];
+        const double frac = ID_BOUNDS_LO[c] + w * t;
+        p[c] = ref[c] + std::fabs(ref[c]) * frac;
+    }
 }
 
 // Identification fitting cost (kite_identification_test.cpp:193-205):

@@ -29,6 +29,29 @@ static void parallel_for(long n, int nthreads, F&& body) {
     for (auto& t : th) t.join();
 }
 
+template <class T>
+static void id_cost_rollout_t(const double* prm, long n, long nsteps, double h, const double* x0, const double* u,
+                              const double* y, const double* p, double* cost, double* xf, int nthreads) {
+    const Params& P = as_params(prm);
+    parallel_for(n, nthreads, [&](long lo, long hi) {
+        for (long i = lo; i < hi; ++i) {
+            T x[13], xn[13], uk[3], pk[21];
+            for (int c = 0; c < 13; ++c) x[c] = T(x0[c]);
+            for (int c = 0; c < 21; ++c) pk[c] = T(p[21 * i + c]);
+            T acc = T(0.0);
+            for (long k = 0; k < nsteps; ++k) {
+                for (int c = 0; c < 3; ++c) uk[c] = T(u[3 * k + c]);
+                rk4_step<T>(P, KITE_ID, x, uk, pk, T(h), xn);
+                for (int c = 0; c < 13; ++c) x[c] = xn[c];
+                T e = T(0.0);
+                for (int c = 0; c < 13; ++c) { T d = T(y[k * 13 + c]) - x[c]; e += T(ID_COST_Q[c]) * (d * d); }
+                acc += e;
+            }
+            cost[i] = (double)(acc * (T(1.0) / T((double)nsteps)));
+            if (xf) for (int c = 0; c < 13; ++c) xf[13 * i + c] = (double)x[c];
+        }
+    });
+}
 extern "C" {
 
 int orc_num_params() { return 39; }
@@ -145,23 +168,16 @@ void orc_ekf_defaults(double* W, double* V) { ekf_default_W(W); ekf_default_V(V)
 // (y[j] = measured state after step j+1), per-sample parameters p[n][21]; id-variant RHS.
 void orc_id_cost_rollout(const double* prm, long n, long nsteps, double h, const double* x0, const double* u,
                          const double* y, const double* p, double* cost, double* xf, int nthreads) {
-    const Params& P = as_params(prm);
-    parallel_for(n, nthreads, [&](long lo, long hi) {
-        for (long i = lo; i < hi; ++i) {
-            double x[13], xn[13];
-            std::memcpy(x, x0, sizeof x);
-            double acc = 0.0;
-            for (long k = 0; k < nsteps; ++k) {
-                rk4_step<double>(P, KITE_ID, x, u + 3 * k, p + 21 * i, h, xn);
-                std::memcpy(x, xn, sizeof x);
-                double e = 0.0;
-                for (int c = 0; c < 13; ++c) { double d = y[k * 13 + c] - x[c]; e += ID_COST_Q[c] * (d * d); }
-                acc += e;
-            }
-            cost[i] = acc * (1.0 / double(nsteps));
-            if (xf) std::memcpy(xf + 13 * i, x, sizeof x);
-        }
-    });
+    id_cost_rollout_t<double>(prm, n, nsteps, h, x0, u, y, p, cost, xf, nthreads);
+}
+// The same rollout in 80-bit extended precision: the yardstick that tells the oracle's own round-off growth over a long
+// horizon apart from an engine error (tests/test_gpu_fullsize.py).
+void orc_id_cost_rollout_ld(const double* prm, long n, long nsteps, double h, const double* x0, const double* u,
+                            const double* y, const double* p, double* cost, double* xf, int nthreads) {
+    id_cost_rollout_t<long double>(prm, n, nsteps, h, x0, u, y, p, cost, xf, nthreads);
+}
+void orc_ekf_update_ld(long n, const double* z, const double* V, double* x, double* P) {
+    for (long i = 0; i < n; ++i) ekf_update_t<long double>(z + 7 * i, V, x + 13 * i, P + 169 * i);
 }
 
 void orc_cheb_points(int P, double* out) { auto v = cheb_points(P); std::memcpy(out, v.data(), v.size() * 8); }
@@ -171,6 +187,9 @@ void orc_cheb_compdiff(int P, int S, double* out) { auto v = cheb_comp_diff_matr
 
 void orc_synth_x0(long traj0, long n, double* x0) { for (long i = 0; i < n; ++i) synth_x0((uint64_t)(traj0 + i), x0 + 13 * i); }
 // u[n][nsteps][3]
+void orc_synth_id_params(long traj0, long n, const double* ref21, double* p) {
+    for (long i = 0; i < n; ++i) synth_id_params((uint64_t)(traj0 + i), ref21, p + 21 * i);
+}
 void orc_synth_controls(long traj0, long n, long nsteps, double* u) {
     for (long i = 0; i < n; ++i)
         for (long k = 0; k < nsteps; ++k) synth_control((uint64_t)(traj0 + i), (uint64_t)k, u + (i * nsteps + k) * 3);

@@ -189,13 +189,24 @@ class Oracle:
         self.lib.orc_ekf_defaults(_p(W), _p(V))
         return W, V
 
-    def id_cost_rollout(self, x0, u, y, p, h, nthreads=1):
+    def ekf_update_ld(self, z, V, x, P):
+        """ekf_update in 80-bit extended precision (conditioning yardstick)."""
+        z = np.ascontiguousarray(np.atleast_2d(z), dtype=np.float64)
+        n = z.shape[0]
+        x = np.array(np.atleast_2d(x), dtype=np.float64, order="C")
+        P = np.array(P, dtype=np.float64, order="C").reshape(n, 13, 13)
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(7, 7)
+        self.lib.orc_ekf_update_ld(C.c_long(n), _p(z), _p(V), _p(x), _p(P))
+        return x, P
+
+    def id_cost_rollout(self, x0, u, y, p, h, nthreads=1, extended=False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64); p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
         n, nsteps = p.shape[0], u.shape[0]
         cost = np.empty(n); xf = np.empty((n, 13))
-        self.lib.orc_id_cost_rollout(_p(self.prm), C.c_long(n), C.c_long(nsteps), C.c_double(h), _p(x0), _p(u), _p(y),
-                                     _p(p), _p(cost), _p(xf), C.c_int(nthreads))
+        fn = self.lib.orc_id_cost_rollout_ld if extended else self.lib.orc_id_cost_rollout
+        fn(_p(self.prm), C.c_long(n), C.c_long(nsteps), C.c_double(h), _p(x0), _p(u), _p(y), _p(p), _p(cost), _p(xf),
+           C.c_int(nthreads))
         return cost, xf
 
     # ---- collocation operators ---------------------------------------------------------
@@ -219,6 +230,10 @@ class Oracle:
     def synth_controls(self, traj0, n, nsteps):
         o = np.empty((n, nsteps, 3)); self.lib.orc_synth_controls(C.c_long(traj0), C.c_long(n), C.c_long(nsteps), _p(o))
         return o
+
+    def synth_id_params(self, traj0, n, ref21):
+        ref = np.ascontiguousarray(ref21, dtype=np.float64); assert ref.shape == (21,)
+        o = np.empty((n, 21)); self.lib.orc_synth_id_params(C.c_long(traj0), C.c_long(n), _p(ref), _p(o)); return o
 
     def flop_counts(self):
         o = (C.c_long * 8)()

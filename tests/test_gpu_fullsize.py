@@ -156,9 +156,11 @@ def test_config5_full_size_id_sweep_and_ekf(okb, params, oracle, golden):
     e = okb.Engine(params, okb.KITE_ID)
     B, N, h = 1 << 20, 2000, 1e-3
     pnom = np.array(golden["rhs_id"]["nominal"]["p"])
-    g = torch.Generator(device="cuda").manual_seed(5)
-    scale = 1 + 0.1 * (2 * torch.rand(21, B, dtype=torch.float64, device="cuda", generator=g) - 1)
-    p = (torch.from_numpy(pnom).cuda().reshape(21, 1) * scale).contiguous()
+    # parameter samples uniform inside the bounds of kite_identification_test.cpp:127-148, keyed on the global sample
+    # index (kite_synth_id_params): the shard of "rank 3 of 8" of the 8,388,608-sample sweep
+    i0 = 3 * B
+    p = e.synth_id_params(B, index0=i0, ref=pnom)
+    assert np.array_equal(aos(p[:, :257]), oracle.synth_id_params(i0, 257, pnom))      # bit-identical to the CPU generator
     p[:, 0] = torch.from_numpy(pnom).cuda()
     x0h = np.array(golden["rollout_config1"]["x0"])
     k = np.arange(N)
@@ -174,12 +176,27 @@ def test_config5_full_size_id_sweep_and_ekf(okb, params, oracle, golden):
     assert bool(torch.isfinite(cost[fin]).all()) and float(cost[fin].min()) >= 0.0
     idx = _sample(np.random.default_rng(3), B, 96)
     ti = torch.from_numpy(idx).cuda()
-    rcost, rxf = oracle.id_cost_rollout(x0h, u, y, aos(p[:, ti]), h, nthreads=8)
+    ps = aos(p[:, ti])
+    rcost, rxf = oracle.id_cost_rollout(x0h, u, y, ps, h, nthreads=8)
     assert np.array_equal(np.isfinite(rxf).all(1), (st[ti] == 0).cpu().numpy())   # same non-finite set
     ok = np.isfinite(rxf).all(1)
-    # sensitivity to the perturbed coefficients over 2 s of flight: relative tolerance on the cost, scaled by its size
-    assert_close(cost[ti].cpu().numpy()[ok], rcost[ok], 1e-7, scale=1e-6, what="config-5 cost")
-    assert_close(aos(out["xf"][:, ti])[ok], rxf[ok], 1e-7, what="config-5 final states")
+    # Tolerance 1e-9 as everywhere.  Two seconds of flight with coefficients up to 50 % off amplify round-off, so the
+    # oracle's own conditioning is MEASURED rather than assumed: the same samples in 80-bit extended precision.  A sample
+    # may exceed 1e-9 only where the double-precision oracle itself is that far from the extended result (x 16).
+    lcost, lxf = oracle.id_cost_rollout(x0h, u, y, ps, h, nthreads=8, extended=True)
+    own_x = np.abs(rxf - lxf) / np.maximum(np.abs(lxf), 1.0)
+    own_c = np.abs(rcost - lcost) / np.maximum(np.abs(lcost), 1e-6)
+    gx = aos(out["xf"][:, ti]); gc = cost[ti].cpu().numpy()
+    err_x = np.abs(gx - lxf) / np.maximum(np.abs(lxf), 1.0)
+    err_c = np.abs(gc - lcost) / np.maximum(np.abs(lcost), 1e-6)
+    print("config-5 sample: oracle double-vs-extended max %.2e (states) %.2e (cost); engine-vs-extended max %.2e / %.2e"
+          % (np.nanmax(own_x[ok]), np.nanmax(own_c[ok]), np.nanmax(err_x[ok]), np.nanmax(err_c[ok])))
+    assert bool((err_x[ok] <= np.maximum(RTOL, 16 * own_x[ok])).all()), "config-5 final states"
+    assert bool((err_c[ok] <= np.maximum(RTOL, 16 * own_c[ok])).all()), "config-5 cost"
+    well = ok & (own_x.max(1) < 1e-11)                               # well-conditioned samples: strict 1e-9 against the oracle
+    assert well.sum() >= len(idx) // 2
+    assert_close(gc[well], rcost[well], RTOL, scale=1e-6, what="config-5 cost")
+    assert_close(gx[well], rxf[well], RTOL, what="config-5 final states")
     e.close()
 
     ek = okb.Engine(params, okb.KITE)

@@ -540,8 +540,18 @@ def test_ekf_predict_vs_oracle_batch(eng, oracle):
     z = x[:, 6:13] + 0.01 * rng.standard_normal((B, 7))
     xu, Pu = eng.ekf_update(soa(z), V, xn.clone(), Pn.clone())
     rxu, rPu = oracle.ekf_update(z, V, rxn, rPn)
-    assert_close(aos(xu), rxu, 1e-8, what="ekf update x")
-    assert_close(aos(Pu, 13, 13), rPu, 1e-8, scale=1e-3, what="ekf update P")
+    # Tolerance 1e-9 where the update is that well conditioned, which is MEASURED per filter: the same update in 80-bit
+    # extended precision tells the oracle's own round-off (7x7 inverse of S = H P H^T + V with V down to 1e-8, then the
+    # cancelling P - K H P) apart from an engine error.  Entries may exceed 1e-9 only by 16 x the oracle's own error.
+    lxu, lPu = oracle.ekf_update_ld(z, V, rxn, rPn)
+    own_x = np.abs(rxu - lxu) / np.maximum(np.abs(lxu), 1.0)
+    own_P = np.abs(rPu - lPu) / np.maximum(np.abs(lPu), 1e-3)
+    err_x = np.abs(aos(xu) - lxu) / np.maximum(np.abs(lxu), 1.0)
+    err_P = np.abs(aos(Pu, 13, 13) - lPu) / np.maximum(np.abs(lPu), 1e-3)
+    print("ekf update: oracle double-vs-extended max %.2e (x) %.2e (P); engine-vs-extended max %.2e / %.2e"
+          % (own_x.max(), own_P.max(), err_x.max(), err_P.max()))
+    assert bool((err_x <= np.maximum(RTOL, 16 * own_x.max(1, keepdims=True))).all()), "ekf update x"
+    assert bool((err_P <= np.maximum(RTOL, 16 * own_P.max((1, 2), keepdims=True))).all()), "ekf update P"
 
 
 def test_id_cost_rollout_vs_oracle(okb, params, oracle, golden):

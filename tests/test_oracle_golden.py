@@ -228,3 +228,24 @@ def test_nmpc_cost_and_gradient(oracle, golden):
     # structure: only r (6..8), theta (13), theta_dot (14) and the controls carry gradient
     gx = g[0, :165].reshape(11, 15)
     assert np.all(gx[:, [0, 1, 2, 3, 4, 5, 9, 10, 11, 12]] == 0.0)
+
+
+def test_flops_header_matches_sources():
+    """openkite_b200/csrc/kite_flops.h (the roofline numerators bench.py reads) is generated by scripts/make_flops.py:
+    the op-counted figures must follow from the CURRENT oracle and device sources (the sympy CSE count is regenerated by
+    the script itself; here only its frozen value is sanity-checked against the survey's figure)."""
+    import importlib.util
+    import os
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_flops", os.path.join(ROOT, "scripts", "make_flops.py"))
+    mf = importlib.util.module_from_spec(spec); spec.loader.exec_module(mf)
+    hdr = mf.read_header()
+    dev = mf.device_counts()
+    orc = mf.oracle_counts()
+    assert hdr["ORACLE_RHS"] == orc["rhs"]["flops"] and hdr["ORACLE_RK4_STEP"] == orc["rk4_step"]["flops"]
+    assert hdr["DEVICE_RHS"] == dev["rhs"]["flops"] and hdr["DEVICE_RK4_STEP"] == dev["rk4_step"]["flops"]
+    assert hdr["DEVICE_RHS_JAC"] == dev["rhs_jac"]["flops"]
+    assert dev["rhs_jac"]["nx"] == hdr["NNZ_JX"] == 104 and dev["rhs_jac"]["nu"] == hdr["NNZ_JU"] == 7
+    assert abs(hdr["ORACLE_RHS_JAC"] - 2690) / 2690 < 0.15            # SURVEY.md 8d figure, own CSE count within 15 %
+    assert abs(hdr["ORACLE_RK4_STEP"] - 1909) / 1909 < 0.02
+    assert hdr["DEVICE_RK4_SENS_STEP"] < hdr["ORACLE_RK4_SENS_STEP"] < hdr["ORACLE_RK4_SENS_STEP_SURVEY"]
