@@ -229,9 +229,10 @@ int kite_rk4_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const dou
     if (rigid && (p_d || u_mode == KITE_U_SYNTH)) return fail(ctx, KITE_ERR_STATE, "kite_rk4_rollout: not valid for rigid body");
     if ((y_d != nullptr) != (cost_d != nullptr)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: y_d and cost_d go together");
     if (traj_d && save_every <= 0) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: save_every must be > 0");
+    if (N >= (1L << 31) || save_every >= (1L << 31)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: N and save_every must be below 2^31");
     if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
-    RolloutArgs a{ctx->K, B, ld, N, h, x0_d, u_d, p_d, xf_d, traj_d, save_every > 0 ? save_every : 1, y_d, cost_d, status_d, index0};
+    RolloutArgs a{ctx->K, B, ld, N, h, h / 6.0, x0_d, u_d, p_d, xf_d, traj_d, save_every > 0 ? save_every : 1, y_d, cost_d, status_d, index0};
     if (rigid && !u_d) { a.u = x0_d; u_mode = 0; }   // controls do not enter the rigid-body RHS; dummy readable pointer
     if (u_mode <= 1) launch_rollout_01(a, u_mode, rigid, p_d != nullptr, ctx->stream);
     else launch_rollout_23(a, u_mode, rigid, p_d != nullptr, ctx->stream);
@@ -494,7 +495,7 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     CK(cudaMemcpyAsync(ctx->small.ptr, W_h, sizeof(double) * 169, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemsetAsync((char*)ctx->counters.ptr + 8, 0, 8, ctx->stream));
-    EkfArgs a{ctx->K, B, ld, dt, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
+    EkfArgs a{ctx->K, B, ld, dt, dt / 6.0, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
               (unsigned long long*)((char*)ctx->counters.ptr + 8)};
     if (ctx->ekf_lines.reserve(ekf_predict_scratch_bytes())) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, (double*)ctx->ekf_lines.ptr, ctx->stream);

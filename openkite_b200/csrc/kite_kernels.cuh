@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_point_eval(const __grid_constant__ Poin
 struct RolloutArgs {
     KiteConsts K;
     long B, ld, N;
-    double h;
+    double h, h6;            // step size and h / 6 (host-computed)
     const double* x0; const double* u; const double* p;
     double* xf; double* traj; long save_every;
     const double* y; double* cost;
@@ -103,6 +103,9 @@ struct RolloutArgs {
     long index0;
 };
 
+#ifndef KITE_PF_INSTR
+#define KITE_PF_INSTR "prefetch.global.L2"
+#endif
 #ifndef KITE_ROLLOUT_BLOCK
 #define KITE_ROLLOUT_BLOCK 128
 #endif
@@ -113,35 +116,70 @@ constexpr int ROLLOUT_BLOCK = KITE_ROLLOUT_BLOCK;
 #define KITE_ROLLOUT_ATTR __launch_bounds__(ROLLOUT_BLOCK, 3)
 #endif
 
+// Global thread index from the special registers, opaque to the optimiser: the rollout recomputes it after the time loop
+// instead of keeping 2 registers alive (or spilled) across the whole horizon.
+__device__ __forceinline__ long fresh_thread_index() {
+    unsigned t, b, n;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
+    asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(n));
+    return (long)b * n + t;
+}
+
+template <int UMODE, bool RIGID, class AC>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A);
+
 template <int UMODE, bool RIGID, bool PERCOEF>
 __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.B) return;
+    // per-trajectory aero coefficients (identification sweeps) live in shared memory, one 21-double record per thread
+    // (odd stride: conflict free): 42 registers the RHS cannot spare (they spilled: 96 B / 80 B per thread in round 1)
+    extern __shared__ __align__(16) unsigned char rollout_smem[];
+    if (fresh_thread_index() >= a.B) return;
     double x[13], u[3];
-    if constexpr (UMODE == 3) {
-        synth_x0((uint64_t)(a.index0 + i), x);
-    } else {
+    {
+        const long i = fresh_thread_index();
+        if constexpr (UMODE == 3) {
+            synth_x0((uint64_t)(a.index0 + i), x);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x0 + (long)c * a.ld + i);
+            for (int c = 0; c < 13; ++c) x[c] = __ldg(a.x0 + (long)c * a.ld + i);
+        }
+        if constexpr (PERCOEF) {
+            AeroCoef At;
+            load_coef(a.K, a.p, a.ld, i, At);
+            reinterpret_cast<AeroCoef*>(rollout_smem)[threadIdx.x] = At;
+        }
     }
-    AeroCoef A = a.K.A;
-    if constexpr (PERCOEF) load_coef(a.K, a.p, a.ld, i, A);
+    if constexpr (PERCOEF) rollout_body<UMODE, RIGID>(a, x, u, reinterpret_cast<const volatile AeroCoef*>(rollout_smem)[threadIdx.x]);
+    else rollout_body<UMODE, RIGID>(a, x, u, a.K.A);
+}
+
+template <int UMODE, bool RIGID, class AC>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A) {
+    const long i = fresh_thread_index();
 
     // Controls of step k.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 2 are pulled into
     // L2 by a register-free prefetch while step k computes, and the (then short-latency) load itself happens at the top
     // of the step -- holding the next step's controls in registers across the step costs 6 registers the RHS needs
     // (measured: 61.5 % instead of 65.0 % of FP64 peak, profiles/r1u).
-    auto load_u = [&](long k, double (&uu)[3]) {
+    // Loop state is kept small on purpose (the RHS leaves no spare registers): a 32-bit step counter and ONE running pointer
+    // per stream instead of 64-bit index arithmetic per step.
+    const int N = (int)a.N;                         // < 2^31 (checked by the host)
+    unsigned lane_id;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane_id));                // re-materialisable anywhere: nothing to keep alive across the loop
+    const bool pf_lane = (lane_id & 15) == 0;
+    const long ustep = 3 * a.ld;
+    const double* up = (UMODE == 1) ? a.u + i : a.u;            // per-trajectory stream / shared log / held control
+    auto load_u = [&](int k, double (&uu)[3]) {
         if constexpr (UMODE == 0) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) uu[c] = __ldg(a.u + (long)c * a.ld + i);
         } else if constexpr (UMODE == 1) {
-            const double* up = a.u + k * 3 * a.ld + i;
 #pragma unroll
             for (int c = 0; c < 3; ++c) uu[c] = __ldg(up + (long)c * a.ld);
         } else if constexpr (UMODE == 2) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) uu[c] = __ldg(a.u + k * 3 + c);
+            for (int c = 0; c < 3; ++c) uu[c] = __ldg(up + c);
         } else {
             synth_control((uint64_t)(a.index0 + i), (uint64_t)k, uu);
         }
@@ -149,39 +187,45 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
     if constexpr (UMODE == 0) load_u(0, u);         // one control per trajectory, held for all steps
     double cost = 0.0;
     const double Qc[13] = {1e3, 1e2, 1e2, 1e2, 1e2, 1e2, 1e1, 1e1, 1e2, 1e2, 1e2, 1e2, 1e2};  // kite_identification_test.cpp:193
-    long next_save = a.save_every;
-    long saved = 0;
-    for (long k = 0; k < a.N; ++k) {
+    const double* yp = a.y;
+    int next_save = (int)a.save_every;
+    for (int k = 0; k < N; ++k) {
         if constexpr (UMODE != 0) {
             load_u(k, u);
             if constexpr (UMODE == 1) {
-                if ((threadIdx.x & 15) == 0 && k + 2 < a.N) {          // one prefetch per 128-byte line
-                    const double* up = a.u + (k + 2) * 3 * a.ld + i;
+                if (pf_lane && k + 2 < N) {                          // one prefetch per 128-byte line
+                    const double* pf = up + 2 * ustep;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(up + (long)c * a.ld));
+                    for (int c = 0; c < 3; ++c) asm volatile(KITE_PF_INSTR " [%0];" :: "l"(pf + (long)c * a.ld));
                 }
+                up += ustep;
+            } else if constexpr (UMODE == 2) {
+                up += 3;
             }
         }
-        rk4_step<RIGID>(a.K, A, x, u, a.h);
-        if (a.y) {                                  // uniform branch: identification cost fused into the rollout
+        rk4_step<RIGID>(a.K, A, x, u, a.h, a.h6);
+        if (yp) {                                   // uniform branch: identification cost fused into the rollout
             double e = 0.0;
 #pragma unroll
             for (int c = 0; c < 13; ++c) {
-                const double dlt = __ldg(a.y + k * 13 + c) - x[c];
+                const double dlt = __ldg(yp + c) - x[c];
                 e = fma(Qc[c] * dlt, dlt, e);
             }
             cost += e;
+            yp += 13;
         }
-        if (a.traj && k + 1 == next_save) {
+        if (a.traj && k + 1 == next_save) {         // rare: the slot and the thread index are recomputed, not kept alive
+            double* const tp = a.traj + (long)(next_save / (int)a.save_every - 1) * 13 * a.ld + fresh_thread_index();
 #pragma unroll
-            for (int c = 0; c < 13; ++c) a.traj[((long)saved * 13 + c) * a.ld + i] = x[c];
-            ++saved; next_save += a.save_every;
+            for (int c = 0; c < 13; ++c) tp[(long)c * a.ld] = x[c];
+            next_save += (int)a.save_every;
         }
     }
+    const long io = fresh_thread_index();
 #pragma unroll
-    for (int c = 0; c < 13; ++c) a.xf[(long)c * a.ld + i] = x[c];
-    if (a.y) a.cost[i] = cost * (1.0 / (double)a.N);
-    if (a.status) a.status[i] = all_finite13(x) ? 0 : 1;
+    for (int c = 0; c < 13; ++c) a.xf[(long)c * a.ld + io] = x[c];
+    if (a.y) a.cost[io] = cost * (1.0 / (double)a.N);
+    if (a.status) a.status[io] = all_finite13(x) ? 0 : 1;
 }
 
 // Fill the synthetic workload buffers (x0 [13][ld], u [N][3][ld]).
@@ -604,7 +648,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 struct EkfArgs {
     KiteConsts K;
     long B, ld;
-    double dt;
+    double dt, dt6;          // step and dt / 6 (host-computed)
     const double* x; const double* u; const double* P;
     double* xn; double* Pn;
     const double* W;         // device [169]
@@ -698,7 +742,7 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
                 SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
                 model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
             }
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
@@ -869,7 +913,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             for (int c = 0; c < 13; ++c) __stcg(Xw + c * 32 + lane, x[c]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) __stcg(Xw + (13 + c) * 32 + lane, u[c]);
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt);
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);

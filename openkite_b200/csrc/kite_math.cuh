@@ -40,6 +40,33 @@ __device__ __forceinline__ double rsqrt_seed(double a) {
 #endif
 }
 
+// High word of a double as a signed integer.  Sign and magnitude tests on it run on the integer pipe (ISETP) and leave the
+// FP64 pipe to the arithmetic: for finite a, hi(a) > 0 <=> a >= 2^-1022 (a positive normal), hi(a) < 0 <=> sign bit set.
+__device__ __forceinline__ int hi_word(double a) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(a);
+#else
+    int64_t b; memcpy(&b, &a, sizeof b); return (int)(b >> 32);
+#endif
+}
+#ifndef KITE_INT_CMP
+#define KITE_INT_CMP 0
+#endif
+__device__ __forceinline__ bool is_pos(double a) {            // a > 0 (denormals count as 0 in the integer form)
+#if KITE_INT_CMP
+    return hi_word(a) > 0;
+#else
+    return a > 0.0;
+#endif
+}
+__device__ __forceinline__ bool is_neg(double a) {            // a < 0
+#if KITE_INT_CMP
+    return hi_word(a) < 0;
+#else
+    return a < 0.0;
+#endif
+}
+
 // 1/a: seed error e0 <= 2^-19  ->  y0 (1 + e + e^2), e = 1 - a y0, error e0^3 <= 2^-57.   MUFU + 3 DFMA.
 __device__ __forceinline__ double fast_rcp(double a) {
     const double y0 = rcp_seed(a);
@@ -114,7 +141,12 @@ __device__ __forceinline__ double asin_poly(double x) {
 // so the polynomial argument never leaves |x| <= 0.7072 and a warp never diverges into libm (random-control
 // rollouts sit at |sideslip| > 37 deg for ~40% of the horizon: profiles/r1f sweep).
 __device__ __forceinline__ double asin_sc(double s, double c) {
+#if KITE_INT_CMP
+    // |s| > 0.70710678 on the high words (0x3FE6A09E = hi(1/sqrt 2); the polynomial is valid up to 0.7072 on either side)
+    const bool big = (hi_word(s) & 0x7fffffff) > 0x3FE6A09E;
+#else
     const bool big = fabs(s) > 0.70710678118654752;
+#endif
     const double r = asin_poly(big ? c : s);
     const double t = (1.5707963267948966 - r) + 6.123233995736766e-17;
     return big ? copysign(t, s) : r;
@@ -124,7 +156,7 @@ __device__ __forceinline__ double asin_sc(double s, double c) {
 __device__ __forceinline__ double atan2_sc(double s, double c) {
     const double r = asin_sc(s, fabs(c));
     const double t = (copysign(3.141592653589793, s) - r) + copysign(1.2246467991473532e-16, s);
-    return (c < 0.0) ? t : r;
+    return is_neg(c) ? t : r;
 }
 
 // logistic(x) = 1 / (1 + exp(-x)); argument clamped to +-700 (result 0 / 1 to within 1e-304 beyond).

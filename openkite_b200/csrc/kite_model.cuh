@@ -18,6 +18,10 @@
 
 #include "kite_math.cuh"
 
+#ifndef KITE_CB_DIRECT
+#define KITE_CB_DIRECT 0
+#endif
+
 namespace kite {
 
 // Derived aerodynamic coefficients (from the 21 raw coefficients, kite.cpp:571-572 order).
@@ -116,25 +120,58 @@ struct NoSink {
 // with compile-time-constant row/col after unrolling, exactly once per structural non-zero
 // (104 + 7 entries when the tether arm is zero, +21 otherwise).
 // =====================================================================================
-template <bool JAC, class Sink>
-__device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A, const double (&x)[13],
-                                          const double (&u)[3], double (&f)[13], Sink& sink) {
+// Everything the right-hand side needs from the control u = [T dE dR]: the five coefficient sums that are affine in dE / dR.
+// RK4 holds u for all four stages (kitemath.cpp:36-51), so the integrators evaluate these once per step, not per stage.
+struct CtrlTerms {
+    double T;        // thrust
+    double cydr;     // CYdr dR                 (side force,  kite.cpp:212)
+    double cl0;      // Cl0 + Cldr dR           (roll moment, kite.cpp:274)
+    double cm0;      // Cm0 + Cmde dE           (pitch moment, kite.cpp:278)
+    double cn0;      // Cn0 + Cndr dR           (yaw moment,  kite.cpp:282)
+    double nzde;     // -CLde dE                (elevator force / (q S), kite.cpp:228)
+};
+template <class AC>
+__device__ __forceinline__ CtrlTerms ctrl_terms(const KiteConsts& K, const AC& A, const double (&u)[3]) {
+    CtrlTerms c;
+    c.T = u[0];
+    c.cydr = A.CYdr * u[2];
+    c.cl0 = fma(A.Cldr, u[2], K.Cl0);
+    c.cm0 = fma(A.Cmde, u[1], A.Cm0);
+    c.cn0 = fma(A.Cndr, u[2], K.Cn0);
+    c.nzde = -A.CLde * u[1];
+    return c;
+}
+
+// AC: AeroCoef, or volatile AeroCoef when the coefficients live in shared memory and must be re-read at every use instead of
+// being hoisted into (and spilled from) registers (identification sweeps, k_rk4_rollout<.., PERCOEF>).
+template <bool JAC, class Sink, class AC>
+__device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, const double (&x)[13],
+                                            const CtrlTerms& uc, double (&f)[13], Sink& sink) {
     const double v[3] = {x[0], x[1], x[2]};
     const double w[3] = {x[3], x[4], x[5]};
     const double r[3] = {x[6], x[7], x[8]};
     const double s = x[9];
     const double a[3] = {x[10], x[11], x[12]};
-    const double dE = u[1], dR = u[2];
 
     // ---- airspeed, angles (lean special functions, kite_math.cuh) ------------------------------
     const double V2 = fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2]));
     const double rV = fast_rsqrt(V2);                         // 1/V (also d V/d v = v rV in the Jacobian)
-    const double V = (V2 > 0.0) ? V2 * rV : 0.0;              // v = 0 is a legal state of the standard model
+    const double V = is_pos(V2) ? V2 * rV : 0.0;              // v = 0 is a legal state of the standard model
     const double iVe = fast_rcp(V + K.eps);
     const double sb = v[1] * iVe;                             // sin(sideslip)
+#if KITE_CB_DIRECT
+    // cos(sideslip) = sqrt(1 - sb^2) = sqrt((V + eps)^2 - v1^2) / (V + eps), and (V + eps)^2 - v1^2 = v0^2 + v2^2 + eps (2 V + eps):
+    // no cancellation near |sb| = 1 and the square root no longer waits for the reciprocal (shorter dependency chain)
+    const double w2 = fma(K.eps, fma(2.0, V, K.eps), fma(v[0], v[0], v[2] * v[2]));
+    const double rw = fast_rsqrt(w2);
+    const double sw = is_pos(w2) ? w2 * rw : 0.0;
+    const double cb = sw * iVe;                               // cos(sideslip) >= 0
+    const double rcb = (V + K.eps) * rw;                      // 1/cos(sideslip)
+#else
     const double c2 = fma(-sb, sb, 1.0);
     const double rcb = fast_rsqrt(c2);                        // 1/cos(sideslip)
-    const double cb = (c2 > 0.0) ? c2 * rcb : 0.0;            // cos(sideslip) >= 0
+    const double cb = is_pos(c2) ? c2 * rcb : 0.0;            // cos(sideslip) >= 0
+#endif
     const double xe = v[0] + K.eps;
     const double irho = fast_rsqrt(fma(xe, xe, v[2] * v[2]));
     const double ca = xe * irho, sa = v[2] * irho;            // cos/sin(angle of attack)
@@ -149,10 +186,10 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     const double CD = fma(CL * CL, K.inv_piAR, A.CD0);
     const double LIFT = fma(CL, qS, A.kLq * V * w[1]);
     const double DRAG = CD * qS;
-    const double cy = fma(A.CYb, ss, A.CYdr * dR);
+    const double cy = fma(A.CYb, ss, uc.cydr);
     const double kYw = fma(A.kYr, w[2], A.kYp * w[0]);
     const double SF = fma(cy, qS, kYw * V);
-    const double Zde = -A.CLde * dE * qS;
+    const double Zde = uc.nzde * qS;
     const double X1 = fma(sa, LIFT, -ca * DRAG);
     const double Z1 = -fma(sa, DRAG, ca * LIFT);
     const double Fx = fma(cb, X1, -sa * Zde);
@@ -184,15 +221,15 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
 
     // ---- v_dot = (Faero + T e1 + R_b)/m + g M^T e3 - w x v ---------------------------------
     const double tm = -tau * K.inv_mass;                              // R_b / mass = tm * m
-    f[0] = fma(tm, m[0], fma(Fx + u[0], K.inv_mass, fma(K.g, M[2][0], fma(w[2], v[1], -w[1] * v[2]))));
+    f[0] = fma(tm, m[0], fma(Fx + uc.T, K.inv_mass, fma(K.g, M[2][0], fma(w[2], v[1], -w[1] * v[2]))));
     f[1] = fma(tm, m[1], fma(Fy, K.inv_mass, fma(K.g, M[2][1], fma(w[0], v[2], -w[2] * v[0]))));
     f[2] = fma(tm, m[2], fma(Fz, K.inv_mass, fma(K.g, M[2][2], fma(w[1], v[0], -w[0] * v[1]))));
 
     // ---- moments ---------------------------------------------------------------------------
     const double qSb = qS * K.b, qSc = qS * K.c;
-    const double cl = fma(A.Clb, ss, fma(A.Cldr, dR, K.Cl0));
-    const double cm = fma(A.Cma, aoa, fma(A.Cmde, dE, A.Cm0));
-    const double cn = fma(A.Cnb, ss, fma(A.Cndr, dR, K.Cn0));
+    const double cl = fma(A.Clb, ss, uc.cl0);
+    const double cm = fma(A.Cma, aoa, uc.cm0);
+    const double cn = fma(A.Cnb, ss, uc.cn0);
     const double klw = fma(A.klr, w[2], A.klp * w[0]);
     const double knw = fma(A.knp, w[0], A.knr * w[2]);
     const double Lm = fma(cl, qSb, klw * V);
@@ -243,7 +280,7 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
             const double dL = fma(dCL, qS, fma(CL, dqS[j], A.kLq * w[1] * dV[j]));
             const double dD = fma(dCDfac * daoa[j], qS, CD * dqS[j]);
             const double dSF = fma(A.CYb * qS, dss[j], fma(cy, dqS[j], kYw * dV[j]));
-            const double dZde = -A.CLde * dE * dqS[j];
+            const double dZde = uc.nzde * dqS[j];
             const double dX1 = fma(-Z1, daoa[j], fma(sa, dL, -ca * dD));
             const double dZ1 = fma(X1, daoa[j], -fma(sa, dD, ca * dL));
             const double dsb = cb * dss[j], dcb = -sb * dss[j];
@@ -430,6 +467,12 @@ __device__ __forceinline__ void kite_eval(const KiteConsts& K, const AeroCoef& A
     }
 }
 
+template <bool JAC, class Sink, class AC>
+__device__ __forceinline__ void kite_eval(const KiteConsts& K, const AC& A, const double (&x)[13],
+                                          const double (&u)[3], double (&f)[13], Sink& sink) {
+    kite_eval_c<JAC>(K, A, x, ctrl_terms(K, A, u), f, sink);
+}
+
 // Rigid-body kinematics (kite.cpp:622-661): v_dot = w_dot = 0.
 template <bool JAC, class Sink>
 __device__ __forceinline__ void rigid_eval(const KiteConsts& K, const double (&x)[13], double (&f)[13], Sink& sink) {
@@ -477,17 +520,36 @@ __device__ __forceinline__ void rigid_eval(const KiteConsts& K, const double (&x
 }
 
 // Model dispatch (RIGID is a compile-time flag so the kite kernels carry no dead code).
-template <bool RIGID, bool JAC, class Sink>
-__device__ __forceinline__ void model_eval(const KiteConsts& K, const AeroCoef& A, const double (&x)[13],
+template <bool RIGID, bool JAC, class Sink, class AC>
+__device__ __forceinline__ void model_eval(const KiteConsts& K, const AC& A, const double (&x)[13],
                                            const double (&u)[3], double (&f)[13], Sink& sink) {
     if constexpr (RIGID) rigid_eval<JAC>(K, x, f, sink);
     else kite_eval<JAC>(K, A, x, u, f, sink);
 }
 
+template <bool RIGID, bool JAC, class Sink, class AC>
+__device__ __forceinline__ void model_eval_c(const KiteConsts& K, const AC& A, const double (&x)[13],
+                                             const CtrlTerms& uc, double (&f)[13], Sink& sink) {
+    if constexpr (RIGID) rigid_eval<JAC>(K, x, f, sink);
+    else kite_eval_c<JAC>(K, A, x, uc, f, sink);
+}
+
+#ifndef KITE_CB_DIRECT
+#define KITE_CB_DIRECT 0
+#endif
+#ifndef KITE_STAGE_UNROLL
+#define KITE_STAGE_UNROLL 1
+#endif
+#ifndef KITE_HOIST_U
+#define KITE_HOIST_U 1
+#endif
+constexpr int STAGE_UNROLL = KITE_STAGE_UNROLL;     // 1: one copy of the RHS in the instruction stream (rolled stage loop)
 // One classical RK4 step in registers (kitemath.cpp:36-51): x <- x + h/6 (k1 + 2 k2 + 2 k3 + k4).
-template <bool RIGID>
-__device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A, double (&x)[13], const double (&u)[3],
-                                         double h) {
+// h6 = h / 6 comes from the host (same correctly rounded quotient): an FP64 division in the time loop costs a MUFU seed,
+// a Newton chain and a slow-path CALL per step.
+template <bool RIGID, class AC>
+__device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, double (&x)[13], const double (&u)[3],
+                                         double h, double h6) {
     // The four stages run as a real loop (one copy of the RHS in the instruction stream: the fully unrolled body
     // was ~100 KB of SASS and stalled on instruction fetch, profiles/r1a_rollout_ncu_summary.txt).
     NoSink ns;
@@ -495,15 +557,21 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AeroCoef& A,
 #pragma unroll
     for (int i = 0; i < 13; ++i) { acc[i] = 0.0; xt[i] = x[i]; }
     const double hh = 0.5 * h;
-#pragma unroll 1
+#if KITE_HOIST_U
+    const CtrlTerms uc = ctrl_terms(K, A, u);                    // the control is held for all four stages
+#endif
+#pragma unroll STAGE_UNROLL
     for (int st = 0; st < 4; ++st) {
+#if KITE_HOIST_U
+        model_eval_c<RIGID, false>(K, A, xt, uc, k, ns);
+#else
         model_eval<RIGID, false>(K, A, xt, u, k, ns);
+#endif
         const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;     // tableau weights b = (1,2,2,1)/6
         const double an = (st == 2) ? h : hh;                    // next stage offset a = (1/2, 1/2, 1)
 #pragma unroll
         for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], x[i]); }
     }
-    const double h6 = h / 6.0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }

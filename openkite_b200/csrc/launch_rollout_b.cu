@@ -4,7 +4,7 @@ template <int UMODE>
 static void go(const RolloutArgs& a, bool rigid, bool percoef, cudaStream_t s) {
     dim3 grid(blocks_for(a.B, ROLLOUT_BLOCK)), block(ROLLOUT_BLOCK);
     if (rigid) k_rk4_rollout<UMODE, true, false><<<grid, block, 0, s>>>(a);
-    else if (percoef) k_rk4_rollout<UMODE, false, true><<<grid, block, 0, s>>>(a);
+    else if (percoef) k_rk4_rollout<UMODE, false, true><<<grid, block, sizeof(AeroCoef) * ROLLOUT_BLOCK, s>>>(a);
     else k_rk4_rollout<UMODE, false, false><<<grid, block, 0, s>>>(a);
 }
 void launch_rollout_23(const RolloutArgs& a, int umode, bool rigid, bool percoef, cudaStream_t s) {

@@ -12,8 +12,8 @@ cap() {   # name regex skip
 }
 for k in $KS; do
   case $k in
-    rollout)  cap rollout 'k_rk4_rollout.*1.*0.*0' 4 ;;      # <1,0,0>: config 2 (3 warm-up + 2 timed: 5th launch)
-    idsweep)  cap idsweep 'k_rk4_rollout.*2.*0.*1' 4 ;;      # <2,0,1>: config 5 (after the B = 1 measurement-log launch)
+    rollout)  cap rollout 'k_rk4_rollout' 4 ;;               # ncu matches the base name: launches 1-5 are <1,0,0> (config 2: 3 warm-up + 2 timed)
+    idsweep)  cap idsweep 'k_rk4_rollout' 9 ;;               # launch 6 = the B = 1 measurement log, 7-11 = <2,0,1> (config 5)
     sensroll) cap sensroll 'k_sens_fused' 1 ;;               # first launches = the 1 M x 10 rollout
     sens)     cap sens 'k_sens_fused' 8 ;;                   # then the single steps
     ekf)      cap ekf 'k_ekf_predict' 2 ;;

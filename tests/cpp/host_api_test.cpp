@@ -134,11 +134,21 @@ int main(int argc, char** argv) {
         DM xe = est2.getEstimation();
         for (int i = 0; i < 7; ++i) CHECK(std::fabs(xe[6 + i] - measurement[i]) < 2e-3);
         CHECK(close_vec(xe, read_vec(gf, "ekf_est"), 1e-8));
-        // Q8: an integrator whose name has neither "RK4" nor "CVODES" leaves the state untouched
+        // Q8 (kiteEKF.cpp:89-97): an integrator whose name has neither "RK4" nor "CVODES" only warns; the covariance is
+        // still propagated with A = I + J dt at the pre-step state, and the state becomes the default-constructed (empty) DM
         Function odd("mystery", {13, 3, 1}, {13}, [](const DMVector& a) { return DMVector{a[0]}; }, kite.context());
         KiteEKF est3(odd, kite.getNumericJacobian());
-        est3.setEstimation(x_est); est3.propagate(dt);
-        CHECK(close_vec(est3.getEstimation(), x_est.nonzeros(), 0.0));
+        est3.setControl(ctl); est3.setEstimation(x_est); est3.propagate(dt);
+        CHECK(est3.getEstimation().numel() == 0);
+        DM Pn3 = est3.getEstimationCovariance();
+        { bool ok = true; for (int i = 0; i < 13; ++i) for (int j = 0; j < 13; ++j) ok = ok && Pn3(i, j) == Pn(i, j); CHECK(ok); }
+        // a CVODES-named integrator is outside the GPU path: loud failure instead of a silently skipped covariance
+        Function cv("CVODES_INT", {13, 3, 1}, {13}, [](const DMVector& a) { return DMVector{a[0]}; }, kite.context());
+        KiteEKF est4(cv, kite.getNumericJacobian());
+        est4.setEstimation(x_est);
+        bool threw_cv = false;
+        try { est4.propagate(dt); } catch (const std::runtime_error&) { threw_cv = true; }
+        CHECK(threw_cv);
     }
 
     // ---- Simulator stepping loop and record formats (simulator.cpp:43-74, simple_logger.cpp:63-85) ----------
