@@ -175,6 +175,21 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
                      const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
                      double* gnorm_d);
 
+/* The same evaluation with the node blocks in SPARSE form: only the structural non-zeros of [d f_s/d x_s | d f_s/d u_s]
+ * (15 x 19 per node) are written, which is how the reference holds AugJacobian (a sparse CasADi matrix in CCS,
+ * kiteNMPF.cpp:169-171) and 2.5x fewer bytes on an HBM-write-bound kernel.
+ *   kite_colloc_nnz_per_node: 113 = 104 (d f/d x) + 7 (d f/d u) + 2 (augmented rows); 134 with a tether arm.
+ *   kite_colloc_sparsity:     row_out[nnz], col_out[nnz] (row 0..14, column 0..18 of the node block) in CCS order
+ *                             (column-major, rows ascending inside a column); returns nnz.  Entry (i, j) of node k is entry
+ *                             (15 k + i, 15 k + j) of d G/d X for j < 15 and (15 k + i, 15 M + 4 k + j - 15) of d G/d U
+ *                             otherwise, each scaled by -tau (the constant part of d G/d z is compD (x) I15).
+ *   JV_d [M * nnz][ld]        value of non-zero s of node k at JV_d[(k * nnz + s) * ld + i]; the other arguments as above. */
+int kite_colloc_nnz_per_node(const kite_ctx* ctx);
+int kite_colloc_sparsity(const kite_ctx* ctx, int* row_out, int* col_out);
+int kite_colloc_eval_sparse(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
+                            const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JV_d,
+                            double* gnorm_d);
+
 /* NMPC performance index and its gradient for B scenarios.
  * Replaces: Chebyshev<SX,P,S,15,4,0>::CollocateCost (chebyshev.hpp:280-333) applied to the Lagrange and Mayer terms
  * of KiteNMPF::createNLP (kiteNMPF.cpp:116-143) -- the NLP objective "f" IPOPT evaluates every iteration:

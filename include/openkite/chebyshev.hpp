@@ -45,6 +45,9 @@ public:
             for (int i = 0; i < 4; ++i) su[i] = Su.size2() > 1 ? Su(i, i) : Su[i];
             const size_t nd = (size_t)NODES * (19 + 15 + 225 + 60) + 1;
             if (kite_ctx_malloc(Ctx->ctx, (void**)&buf, sizeof(double) * nd) != 0) throw std::runtime_error("Collocated: device allocation failed");
+            nnz_ = kite_colloc_nnz_per_node(Ctx->ctx);
+            prow_.resize((size_t)nnz_); pcol_.resize((size_t)nnz_);
+            if (kite_colloc_sparsity(Ctx->ctx, prow_.data(), pcol_.data()) != nnz_) throw std::runtime_error("Collocated: sparsity query failed");
         }
         ~Collocated() { if (buf) kite_ctx_free(Ctx->ctx, buf); }
         Collocated(const Collocated&) = delete;
@@ -55,39 +58,83 @@ public:
         DM Jacobian(const DM& z) { DM g, j; eval(z, g, j, true); return j; }
         void eval(const DM& z, DM& Gout, DM& Jout, bool want_jac = true) {
             const int M = NODES;
-            if (z.numel() != M * 19) throw std::invalid_argument("Collocated::eval: z must have NODES*(15+4) elements");
-            double* z_d = buf; double* G_d = z_d + M * 19; double* JX_d = G_d + M * 15; double* JU_d = JX_d + M * 225; double* gn_d = JU_d + M * 60;
-            Ctx->h2d(z_d, z.ptr(), (size_t)M * 19);
-            Ctx->check(kite_colloc_eval(Ctx->ctx, 1, 1, M, compD_rm.data(), tau_, sx, su, z_d, nullptr, G_d, want_jac ? JX_d : nullptr,
-                                        want_jac ? JU_d : nullptr, gn_d), "kite_colloc_eval");
-            Gout = DM(M * 15, 1);
-            Ctx->d2h(Gout.ptr(), G_d, (size_t)M * 15);
+            std::vector<double> jv;
+            eval_values(z, Gout, jv, want_jac);
             if (!want_jac) return;
-            std::vector<double> jx((size_t)M * 225), ju((size_t)M * 60);
-            Ctx->d2h(jx.data(), JX_d, jx.size()); Ctx->d2h(ju.data(), JU_d, ju.size());
-            // assemble: [kron(CompD, I15) - tau blkdiag(JX_k) | -tau blkdiag(JU_k)]
+            // assemble the dense matrix from the structural non-zeros: [kron(CompD, I15) - tau blkdiag(JX_k) | -tau blkdiag(JU_k)]
             Jout = DM(M * 15, M * 19);
             for (int k = 0; k < M; ++k) {
                 for (int l = 0; l < M; ++l) { double v = compd_(k, l); if (v != 0.0) for (int i = 0; i < 15; ++i) Jout(k * 15 + i, l * 15 + i) = v; }
-                for (int i = 0; i < 15; ++i) {
-                    for (int j = 0; j < 15; ++j) Jout(k * 15 + i, k * 15 + j) -= tau_ * jx[(size_t)k * 225 + i * 15 + j];
-                    for (int j = 0; j < 4; ++j) Jout(k * 15 + i, M * 15 + k * 4 + j) = -tau_ * ju[(size_t)k * 60 + i * 4 + j];
+                for (int s = 0; s < nnz_; ++s) {
+                    const int i = prow_[s], j = pcol_[s];
+                    const double v = -tau_ * jv[(size_t)k * nnz_ + s];
+                    if (j < 15) Jout(k * 15 + i, k * 15 + j) += v;
+                    else Jout(k * 15 + i, M * 15 + k * 4 + (j - 15)) = v;
                 }
             }
         }
+        /** AugJacobian in compressed-column storage, the form the reference holds it in (a sparse casadi::SX Jacobian,
+         *  kiteNMPF.cpp:169-171): colptr [NODES*19 + 1], rowind [nnz], values [nnz].  The pattern is the union of
+         *  kron(CompD, I15) and the per-node structural non-zeros; it does not depend on z. */
+        void JacobianCCS(const DM& z, std::vector<int>& colptr, std::vector<int>& rowind, std::vector<double>& values) {
+            const int M = NODES;
+            DM g; std::vector<double> jv;
+            eval_values(z, g, jv, true);
+            colptr.assign((size_t)M * 19 + 1, 0); rowind.clear(); values.clear();
+            for (int col = 0; col < M * 19; ++col) {
+                const bool isx = col < M * 15;
+                const int k = isx ? col / 15 : (col - M * 15) / 4;          // node owning this column's varying block
+                const int jl = isx ? col % 15 : 15 + (col - M * 15) % 4;    // column inside the 15 x 19 node block
+                for (int row = 0; row < M * 15; ++row) {
+                    const int kr = row / 15, il = row % 15;
+                    double v = 0.0; bool nz = false;
+                    if (isx && il == jl && compd_(kr, k) != 0.0) { v = compd_(kr, k); nz = true; }
+                    if (kr == k) {
+                        for (int s = 0; s < nnz_; ++s)
+                            if (prow_[s] == il && pcol_[s] == jl) { v -= tau_ * jv[(size_t)k * nnz_ + s]; nz = true; break; }
+                    }
+                    if (nz) { rowind.push_back(row); values.push_back(v); }
+                }
+                colptr[(size_t)col + 1] = (int)rowind.size();
+            }
+        }
+        /** structural non-zeros per node block and their (row, column) inside the 15 x 19 block, CCS order */
+        int nnz_per_node() const { return nnz_; }
+        const std::vector<int>& pattern_rows() const { return prow_; }
+        const std::vector<int>& pattern_cols() const { return pcol_; }
         /** batched device entry point (config 4): see kite_colloc_eval in include/kite_b200.h */
         void eval_device(long B, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d, double* gnorm_d) {
             Ctx->check(kite_colloc_eval(Ctx->ctx, B, B, NODES, compD_rm.data(), tau_, sx, su, z_d, p_d, G_d, JX_d, JU_d, gnorm_d), "kite_colloc_eval");
         }
+        /** the same with sparse node blocks: JV_d [NODES * nnz_per_node()][B] */
+        void eval_device_sparse(long B, const double* z_d, const double* p_d, double* G_d, double* JV_d, double* gnorm_d) {
+            Ctx->check(kite_colloc_eval_sparse(Ctx->ctx, B, B, NODES, compD_rm.data(), tau_, sx, su, z_d, p_d, G_d, JV_d, gnorm_d), "kite_colloc_eval_sparse");
+        }
         double tau() const { return tau_; }
 
     private:
+        /** G and the structural non-zeros of the node blocks ([NODES][nnz]) through kite_colloc_eval_sparse (B = 1) */
+        void eval_values(const DM& z, DM& Gout, std::vector<double>& jv, bool want_jac) {
+            const int M = NODES;
+            if (z.numel() != M * 19) throw std::invalid_argument("Collocated::eval: z must have NODES*(15+4) elements");
+            double* z_d = buf; double* G_d = z_d + M * 19; double* JV_d = G_d + M * 15; double* gn_d = JV_d + M * 285;
+            Ctx->h2d(z_d, z.ptr(), (size_t)M * 19);
+            if (want_jac) Ctx->check(kite_colloc_eval_sparse(Ctx->ctx, 1, 1, M, compD_rm.data(), tau_, sx, su, z_d, nullptr, G_d, JV_d, gn_d), "kite_colloc_eval_sparse");
+            else Ctx->check(kite_colloc_eval(Ctx->ctx, 1, 1, M, compD_rm.data(), tau_, sx, su, z_d, nullptr, G_d, nullptr, nullptr, gn_d), "kite_colloc_eval");
+            Gout = DM(M * 15, 1);
+            Ctx->d2h(Gout.ptr(), G_d, (size_t)M * 15);
+            if (!want_jac) return;
+            jv.resize((size_t)M * nnz_);
+            Ctx->d2h(jv.data(), JV_d, jv.size());
+        }
         std::shared_ptr<KiteContext> Ctx;
         std::vector<double> compD_rm;
         double tau_;
         DM compd_;
         double sx[15], su[4];
         double* buf = nullptr;
+        int nnz_ = 0;
+        std::vector<int> prow_, pcol_;
     };
 
     /** chebyshev.hpp:241-271 with the scaled augmented kite ODE of kiteNMPF.cpp:100-107 as `dynamics`. */

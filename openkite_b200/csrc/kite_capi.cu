@@ -419,14 +419,13 @@ int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, cons
 }
 
 // ---------------------------------------------------------------- collocation ---------------------
-int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
-                     const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
-                     double* gnorm_d) {
+static int colloc_eval_impl(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
+                            const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
+                            double* gnorm_d, bool sparse, const char* who) {
     if (ctx && B == 0) return KITE_OK;
-    if (!ctx || B < 0 || ld < B || M < 2 || M > 1024 || !compD_h || !sx_h || !su_h || !z_d || !G_d)
-        return fail(ctx, KITE_ERR_ARG, "kite_colloc_eval: bad argument");
-    if (ctx->model_kind == KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_STATE, "kite_colloc_eval: kite models only");
-    if (B == 0) return KITE_OK;
+    if (!ctx || B < 0 || ld < B || M < 2 || M > 1024 || !compD_h || !sx_h || !su_h || !z_d || !G_d || (sparse && !JX_d))
+        return fail(ctx, KITE_ERR_ARG, std::string(who) + ": bad argument");
+    if (ctx->model_kind == KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_STATE, std::string(who) + ": kite models only");
     CK(cudaSetDevice(ctx->device));
     if (ctx->small.reserve(sizeof(double) * (size_t)M * M + 4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemcpyAsync(ctx->small.ptr, compD_h, sizeof(double) * (size_t)M * M, cudaMemcpyHostToDevice, ctx->stream));
@@ -436,9 +435,32 @@ int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_
     for (int i = 0; i < 4; ++i) { a.su[i] = su_h[i]; a.isu[i] = 1.0 / su_h[i]; }
     a.compD = (const double*)ctx->small.ptr;
     a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d;
-    launch_colloc_eval(a, p_d != nullptr, ctx->stream);
+    launch_colloc_eval(a, p_d != nullptr, sparse ? (ctx->K.has_arm ? 2 : 1) : 0, ctx->stream);
     LAUNCH_CHECK("k_colloc_eval");
     return KITE_OK;
+}
+
+int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
+                     const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
+                     double* gnorm_d) {
+    return colloc_eval_impl(ctx, B, ld, M, compD_h, tau, sx_h, su_h, z_d, p_d, G_d, JX_d, JU_d, gnorm_d, false, "kite_colloc_eval");
+}
+
+int kite_colloc_nnz_per_node(const kite_ctx* ctx) {
+    if (!ctx) return KITE_ERR_ARG;
+    return ctx->K.has_arm ? COLLOC_NNZ_ARM : COLLOC_NNZ_NOARM;
+}
+int kite_colloc_sparsity(const kite_ctx* ctx, int* row_out, int* col_out) {
+    if (!ctx || !row_out || !col_out) return KITE_ERR_ARG;
+    const CollocTab t = make_colloc_tab(ctx->K.has_arm != 0);
+    for (int j = 0; j < 19; ++j)
+        for (int i = 0; i < 15; ++i)
+            if (t.slot[i][j] >= 0) { row_out[t.slot[i][j]] = i; col_out[t.slot[i][j]] = j; }
+    return t.nnz;
+}
+int kite_colloc_eval_sparse(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
+                            const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JV_d, double* gnorm_d) {
+    return colloc_eval_impl(ctx, B, ld, M, compD_h, tau, sx_h, su_h, z_d, p_d, G_d, JV_d, nullptr, gnorm_d, true, "kite_colloc_eval_sparse");
 }
 
 int kite_colloc_cost(kite_ctx* ctx, long B, long ld, int P, int S, const double* qw_h, double tau, const double* sx_h,

@@ -1124,17 +1124,66 @@ struct CollocSink {
     __device__ __forceinline__ void ju(int i, int j, double v) const { if (jup) jup[(long)(i * 4 + j) * ld] = sx[i] * v * isu[j]; }
 };
 
-template <bool PERCOEF, int NPB>
+// ---- compact node blocks: structural non-zeros only, in CCS (column-major) order ------------------------------------
+// The reference's AugJacobian is a SPARSE CasADi matrix (kiteNMPF.cpp:169-171): per node it carries the 104 (+ 21 with a
+// tether arm) non-zeros of d f / d x, the 7 of d f / d u and the two constant entries of the augmented rows
+// (theta_dot = V1: (13, 14); V1_dot = u_v: (14, 15 + 3)).  Slot numbering = position in a column-major walk over the
+// 15 x 19 node block [d f_s / d x_s | d f_s / d u_s]; the same table answers kite_colloc_sparsity().
+__host__ __device__ constexpr bool colloc_nz(int i, int j, bool arm) {       // i in 0..14, j in 0..18
+    if (j < 15) {
+        if (i < 13 && j < 13) return jx_nz(i, j, arm);
+        return i == 13 && j == 14;
+    }
+    if (i < 13 && j - 15 < 3) return ju_nz(i, j - 15);
+    return i == 14 && j == 18;
+}
+struct CollocTab { int slot[15][19]; int nnz; };
+constexpr CollocTab make_colloc_tab(bool arm) {
+    CollocTab t{};
+    int s = 0;
+    for (int j = 0; j < 19; ++j)
+        for (int i = 0; i < 15; ++i) t.slot[i][j] = colloc_nz(i, j, arm) ? s++ : -1;
+    t.nnz = s;
+    return t;
+}
+__device__ constexpr CollocTab COLLOC_TAB_NOARM = make_colloc_tab(false);
+__device__ constexpr CollocTab COLLOC_TAB_ARM = make_colloc_tab(true);
+constexpr int COLLOC_NNZ_NOARM = make_colloc_tab(false).nnz, COLLOC_NNZ_ARM = make_colloc_tab(true).nnz;
+static_assert(COLLOC_NNZ_NOARM == 104 + 7 + 2 && COLLOC_NNZ_ARM == 125 + 7 + 2, "node-block non-zeros");
+
+template <bool ARM>
+struct CollocSparseSink {       // value of entry (i, j) of the node block goes to row slot(i, j) of the node's [nnz][ld] slab
+    double* jv; long ld;
+    const double* sx; const double* isx; const double* isu;
+    __device__ __forceinline__ void jx(int i, int j, double v) const {
+        const int sl = (ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[i][j];
+        if (sl >= 0) jv[(long)sl * ld] = sx[i] * v * isx[j];
+    }
+    __device__ __forceinline__ void ju(int i, int j, double v) const {
+        const int sl = (ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[i][15 + j];
+        if (sl >= 0) jv[(long)sl * ld] = sx[i] * v * isu[j];
+    }
+};
+
+// FMT 0: dense 15 x 15 / 15 x 4 node blocks (JX, JU);  1 / 2: structural non-zeros only (JV), without / with tether arm.
+template <bool PERCOEF, int NPB, int FMT>
 __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant__ CollocArgs a) {
     __shared__ double red[NPB][32];                // partial ||G||^2 per node row of the block
+    // per-scenario aero coefficients live in shared memory (one 21-double record per thread, re-read at every use): held in
+    // registers they pushed the Jacobian code over the 255-register limit (136 B / 184 B of spills in round 1)
+    __shared__ AeroCoef coef_sh[PERCOEF ? 32 * NPB : 1];
     const int lane = threadIdx.x;
     const int ky = threadIdx.y;
     const long s = (long)blockIdx.x * 32 + lane;
     const int M = a.M;
     double g2 = 0.0;
     if (s < a.B) {
-        AeroCoef A = a.K.A;
-        if constexpr (PERCOEF) load_coef(a.K, a.p, a.ld, s, A);
+        if constexpr (PERCOEF) {
+            AeroCoef At;
+            load_coef(a.K, a.p, a.ld, s, At);
+            coef_sh[ky * 32 + lane] = At;
+        }
+        const volatile AeroCoef& Av = coef_sh[PERCOEF ? ky * 32 + lane : 0];
         for (int k = ky; k < M; k += NPB) {
             double x[13], u[3], f[13];
             const double* zx = a.z + (long)(k * 15) * a.ld + s;
@@ -1145,32 +1194,43 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 3; ++c) u[c] = a.isu[c] * __ldg(zu + (long)c * a.ld);
             const double u3 = a.isu[3] * __ldg(zu + 3L * a.ld);
-            CollocSink sink{a.JX ? a.JX + (long)(k * 225) * a.ld + s : nullptr,
-                            a.JU ? a.JU + (long)(k * 60) * a.ld + s : nullptr, a.ld, a.sx, a.isx, a.isu};
-            kite_eval<true>(a.K, A, x, u, f, sink);
-            // augmented rows: theta_dot = V1 (x[14]), V1_dot = u_v (u[3])   (kiteNMPF.cpp:62-73)
-            if (a.JX) sink.jxp[(long)(13 * 15 + 14) * a.ld] = a.sx[13] * a.isx[14];
-            if (a.JU) sink.jup[(long)(14 * 4 + 3) * a.ld] = a.sx[14] * a.isu[3];
-            // structural zeros of the dense node blocks are written here, once, instead of a memset pass over the
-            // 25 KB/scenario output beforehand (the kernel is HBM-write bound: every byte is stored exactly once)
-            if (a.JX) {
-                const bool arm = a.K.has_arm != 0;
+            if constexpr (FMT == 0) {
+                CollocSink sink{a.JX ? a.JX + (long)(k * 225) * a.ld + s : nullptr,
+                                a.JU ? a.JU + (long)(k * 60) * a.ld + s : nullptr, a.ld, a.sx, a.isx, a.isu};
+                if constexpr (PERCOEF) kite_eval<true>(a.K, Av, x, u, f, sink);
+                else kite_eval<true>(a.K, a.K.A, x, u, f, sink);
+                // augmented rows: theta_dot = V1 (x[14]), V1_dot = u_v (u[3])   (kiteNMPF.cpp:62-73)
+                if (a.JX) sink.jxp[(long)(13 * 15 + 14) * a.ld] = a.sx[13] * a.isx[14];
+                if (a.JU) sink.jup[(long)(14 * 4 + 3) * a.ld] = a.sx[14] * a.isu[3];
+                // structural zeros of the dense node blocks are written here, once, instead of a memset pass over the
+                // 25 KB/scenario output beforehand (the kernel is HBM-write bound: every byte is stored exactly once)
+                if (a.JX) {
+                    const bool arm = a.K.has_arm != 0;
 #pragma unroll
-                for (int i = 0; i < 15; ++i)
+                    for (int i = 0; i < 15; ++i)
 #pragma unroll
-                    for (int j = 0; j < 15; ++j) {
-                        const bool kite_blk = (i < 13 && j < 13);
-                        const bool nz_noarm = kite_blk ? jx_nz(i, j, false) : (i == 13 && j == 14);
-                        const bool nz_arm = kite_blk ? jx_nz(i, j, true) : (i == 13 && j == 14);
-                        if (!nz_arm || (!nz_noarm && !arm)) sink.jxp[(long)(i * 15 + j) * a.ld] = 0.0;
-                    }
-            }
-            if (a.JU) {
+                        for (int j = 0; j < 15; ++j) {
+                            const bool kite_blk = (i < 13 && j < 13);
+                            const bool nz_noarm = kite_blk ? jx_nz(i, j, false) : (i == 13 && j == 14);
+                            const bool nz_arm = kite_blk ? jx_nz(i, j, true) : (i == 13 && j == 14);
+                            if (!nz_arm || (!nz_noarm && !arm)) sink.jxp[(long)(i * 15 + j) * a.ld] = 0.0;
+                        }
+                }
+                if (a.JU) {
 #pragma unroll
-                for (int i = 0; i < 15; ++i)
+                    for (int i = 0; i < 15; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (!((i < 13 && j < 3) ? ju_nz(i, j) : (i == 14 && j == 3))) sink.jup[(long)(i * 4 + j) * a.ld] = 0.0;
+                        for (int j = 0; j < 4; ++j)
+                            if (!((i < 13 && j < 3) ? ju_nz(i, j) : (i == 14 && j == 3))) sink.jup[(long)(i * 4 + j) * a.ld] = 0.0;
+                }
+            } else {
+                constexpr bool ARM = (FMT == 2);
+                constexpr int NNZ = ARM ? COLLOC_NNZ_ARM : COLLOC_NNZ_NOARM;
+                CollocSparseSink<ARM> sink{a.JX + (long)(k * NNZ) * a.ld + s, a.ld, a.sx, a.isx, a.isu};
+                if constexpr (PERCOEF) kite_eval<true>(a.K, Av, x, u, f, sink);
+                else kite_eval<true>(a.K, a.K.A, x, u, f, sink);
+                sink.jv[(long)(ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[13][14] * a.ld] = a.sx[13] * a.isx[14];
+                sink.jv[(long)(ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[14][18] * a.ld] = a.sx[14] * a.isu[3];
             }
             double fa[15];
 #pragma unroll

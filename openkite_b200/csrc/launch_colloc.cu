@@ -3,11 +3,19 @@
 #define KITE_COLLOC_NPB 4      // node rows per CTA: 128 threads at 255 registers, no spills (11 rows = 352 threads spilled 400+ B)
 #endif
 namespace kite {
-void launch_colloc_eval(const CollocArgs& a, bool percoef, cudaStream_t s) {
+void launch_colloc_eval(const CollocArgs& a, bool percoef, int fmt, cudaStream_t s) {
     const unsigned gb = blocks_for(a.B, 32);
     dim3 block(32, KITE_COLLOC_NPB);
-    if (percoef) k_colloc_eval<true, KITE_COLLOC_NPB><<<gb, block, 0, s>>>(a);
-    else k_colloc_eval<false, KITE_COLLOC_NPB><<<gb, block, 0, s>>>(a);
+    constexpr int N = KITE_COLLOC_NPB;
+    if (percoef) {
+        if (fmt == 0) k_colloc_eval<true, N, 0><<<gb, block, 0, s>>>(a);
+        else if (fmt == 1) k_colloc_eval<true, N, 1><<<gb, block, 0, s>>>(a);
+        else k_colloc_eval<true, N, 2><<<gb, block, 0, s>>>(a);
+    } else {
+        if (fmt == 0) k_colloc_eval<false, N, 0><<<gb, block, 0, s>>>(a);
+        else if (fmt == 1) k_colloc_eval<false, N, 1><<<gb, block, 0, s>>>(a);
+        else k_colloc_eval<false, N, 2><<<gb, block, 0, s>>>(a);
+    }
 }
 void launch_colloc_cost(const CostArgs& a, cudaStream_t s) {
     dim3 block(32, 4);

@@ -104,6 +104,9 @@ def load_library():
     L.kite_rk4_sens_step.argtypes = [vp, lg, lg, db, dp, dp, dp, dp, dp, dp]
     L.kite_rk4_sens_rollout.argtypes = [vp, lg, lg, lg, db, dp, dp, dp, dp, dp, dp]
     L.kite_colloc_eval.argtypes = [vp, lg, lg, ip, dp, db, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.kite_colloc_eval_sparse.argtypes = [vp, lg, lg, ip, dp, db, dp, dp, dp, dp, dp, dp, dp]
+    L.kite_colloc_nnz_per_node.argtypes = [vp]
+    L.kite_colloc_sparsity.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.kite_colloc_cost.argtypes = [vp, lg, lg, ip, ip, dp, db, dp, C.POINTER(NmpcCost), dp, dp, dp]
     L.kite_ekf_work_bytes.argtypes = [lg]; L.kite_ekf_work_bytes.restype = C.c_size_t
     L.kite_ekf_predict_batch.argtypes = [vp, lg, lg, db, dp, dp, dp, dp, dp, dp, dp]
@@ -301,6 +304,30 @@ class Engine:
         self._ck(self.L.kite_colloc_eval(self.ctx, B, B, M, cdp, tau, sxp, sup, _ptr(z), _ptr(p), _ptr(G), _ptr(JX),
                                          _ptr(JU), _ptr(gn)))
         return G, JX, JU, gn
+
+    def colloc_nnz_per_node(self):
+        return int(self.L.kite_colloc_nnz_per_node(self.ctx))
+
+    def colloc_sparsity(self):
+        """(rows, cols) of the structural non-zeros of a 15 x 19 node block [d f_s/d x_s | d f_s/d u_s], CCS order."""
+        n = self.colloc_nnz_per_node()
+        r, c = (C.c_int * n)(), (C.c_int * n)()
+        assert self.L.kite_colloc_sparsity(self.ctx, r, c) == n
+        return list(r), list(c)
+
+    def colloc_eval_sparse(self, z, M, compD, tau, sx, su, p=None, want_norm=True, out=None):
+        """As colloc_eval, node blocks as structural non-zeros: returns G [M*15, B], JV [M*nnz, B], gnorm [B]."""
+        self._use_torch_stream()
+        B = z.shape[1]
+        self._chk(z, M * 19)
+        cd, cdp = _hostarr(compD); sxa, sxp = _hostarr(sx); sua, sup = _hostarr(su)
+        if out is not None:
+            G, JV, gn = out
+        else:
+            G, JV = self.empty(M * 15, B), self.empty(M * self.colloc_nnz_per_node(), B)
+            gn = self.empty(B) if want_norm else None
+        self._ck(self.L.kite_colloc_eval_sparse(self.ctx, B, B, M, cdp, tau, sxp, sup, _ptr(z), _ptr(p), _ptr(G), _ptr(JV), _ptr(gn)))
+        return G, JV, gn
 
     def colloc_cost(self, z, P, S, qw, tau, sx, cost_params, want_grad=True, out=None):
         """NMPC performance index + gradient (kite_colloc_cost): z [M*19, B] -> cost [B], grad [M*19, B]."""

@@ -190,6 +190,21 @@ int main(int argc, char** argv) {
         bool ok = J.size1() == 165 && J.size2() == 209;
         for (int i = 0; ok && i < 165; ++i) for (int j = 0; j < 209; ++j) if (std::fabs(J(i, j) - Jref[(size_t)i * 209 + j]) > 1e-9 * std::fmax(1.0, std::fabs(Jref[(size_t)i * 209 + j]))) { ok = false; std::printf("  J mismatch %d %d\n", i, j); break; }
         CHECK(ok);
+        // the same matrix in the reference's own storage (sparse CCS, kiteNMPF.cpp:169-171): 113 structural non-zeros per
+        // node block + the off-block entries of kron(CompD, I15); expanding it must reproduce the dense matrix exactly
+        CHECK(coll->nnz_per_node() == 113);
+        std::vector<int> colptr, rowind; std::vector<double> vals;
+        coll->JacobianCCS(DM(z), colptr, rowind, vals);
+        CHECK(colptr.size() == 210 && colptr.back() == (int)vals.size());
+        DM Jd(165, 209);
+        bool sorted = true;
+        for (int c = 0; c < 209; ++c)
+            for (int t = colptr[c]; t < colptr[c + 1]; ++t) { Jd(rowind[t], c) = vals[t]; if (t > colptr[c] && rowind[t] <= rowind[t - 1]) sorted = false; }
+        CHECK(sorted);
+        bool same = true; int nz_dense = 0;
+        for (int i = 0; i < 165; ++i) for (int j = 0; j < 209; ++j) { same = same && Jd(i, j) == J(i, j); nz_dense += (J(i, j) != 0.0); }
+        CHECK(same);
+        CHECK((int)vals.size() >= nz_dense && (int)vals.size() < 165 * 209 / 8);
         // performance index of the path-following NMPC (kiteNMPF.cpp:116-143), path of nmpf_node.cpp:31-39
         std::vector<double> cref = read_vec(gf, "nmpc_cost"), gref = read_vec(gf, "nmpc_grad");
         DM q_rot{std::cos(M_PI / 8), 0.0, std::sin(M_PI / 8), 0.0};

@@ -525,6 +525,40 @@ def test_nmpc_cost_vs_oracle_batch(eng, okb, oracle, golden):
     assert none is None and abs(cost1.item() - rcost[0]) <= RTOL * abs(rcost[0])
 
 
+def test_colloc_sparse_blocks_match_dense(okb, params, oracle, golden):
+    """The sparse node-block output (structural non-zeros in CCS order, the storage of the reference's AugJacobian,
+    kiteNMPF.cpp:169-171) carries bitwise the values of the dense blocks, and nothing else in them is non-zero -- without
+    and with a tether arm, nominal and per-scenario coefficients."""
+    from openkite_b200.collocation import comp_diff_matrix
+    import copy
+    c = golden["colloc_nmpc_P5_S2_scaled"]
+    M, B = 11, 77
+    rng = np.random.default_rng(12)
+    z = soa(np.array(c["z"])[None, :] * (1 + 0.05 * rng.standard_normal((B, 209))))
+    pnom = np.array(golden["rhs_id"]["nominal"]["p"])
+    pb = soa(pnom[None, :] * (1 + 0.1 * (2 * rng.random((B, 21)) - 1)))
+    compD = comp_diff_matrix(5, 2)
+    for arm in (None, (0.02, -0.01, 0.03)):
+        prm = copy.copy(params)
+        if arm:
+            prm.rx, prm.ry, prm.rz = arm
+        e = okb.Engine(prm, okb.KITE)
+        nnz = e.colloc_nnz_per_node()
+        assert nnz == (134 if arm else 113)
+        rows, cols = e.colloc_sparsity()
+        assert len(rows) == nnz and sorted(zip(cols, rows)) == list(zip(cols, rows))        # CCS: columns, then rows, ascending
+        for p in (None, pb):
+            G, JX, JU, gn = e.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], p=p)
+            G2, JV, gn2 = e.colloc_eval_sparse(z, M, compD, 0.25, c["sx"], c["su"], p=p)
+            assert torch.equal(G, G2) and torch.equal(gn, gn2)
+            dense = torch.cat([JX.reshape(M, 15, 15, B), JU.reshape(M, 15, 4, B)], dim=2)       # [M, 15, 19, B]
+            picked = dense[:, rows, cols, :]                                                    # [M, nnz, B]
+            assert torch.equal(picked.reshape(M * nnz, B), JV)
+            mask = torch.zeros(15, 19, dtype=torch.bool, device="cuda"); mask[rows, cols] = True
+            assert float(dense[:, ~mask, :].abs().max()) == 0.0                                 # everything else is a structural zero
+        e.close()
+
+
 def test_ekf_predict_vs_oracle_batch(eng, oracle):
     B, dt = 515, 0.0084
     x = oracle.synth_x0(0, B); u = oracle.synth_controls(0, B, 1)[:, 0, :]
