@@ -102,11 +102,20 @@ int kite_copy_d2h(kite_ctx* ctx, void* dst_h, const void* src_d, size_t bytes);
 /* Replaces: Function "dynamics"(x,u[,p]) -> xdot   kite.cpp:324 / :575.   p_d may be NULL. */
 int kite_rhs_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d,
                    double* f_d);
+/* Replaces: Function "Aero"(x,u) -> body-frame aerodynamic force Faero_b (3)   kite.cpp:224-234, :330
+ * (KiteDynamics::getAeroDynamicForces, kite.h:126).  F_d [3][ld]. */
+int kite_aero_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d,
+                    double* F_d);
 /* Replaces: Function "dyn_jacobian"(x,u[,p]) -> d f/d x (13x13)   kite.cpp:327-328 / :578-579.
  * Also returns d f/d u (13x3), which the reference only exposes inside AugJacobian (kiteNMPF.cpp:169-171).
  * Jx_d: [169][ld], Ju_d: [39][ld] (either may be NULL). */
 int kite_jac_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d,
                    double* Jx_d, double* Ju_d);
+
+/* Structural non-zeros of d f/d x (wrt_u = 0; 104, or 125 with a tether arm; 49 for the rigid body) or d f/d u (wrt_u = 1;
+ * 7) in compressed-column order: row_out[nnz], col_out[nnz] (either may be NULL to only count); returns nnz.  This is the
+ * sparsity the reference's SX::jacobian yields (kite.cpp:327-328).  Needs no context and no GPU. */
+int kite_jac_sparsity(int model_kind, int has_arm, int wrt_u, int* row_out, int* col_out);
 
 /* ---------------------------------------------------------------- RK4 ------------------- */
 /* Replaces: Function "RK4"(X,U,dT) kite.cpp:332-338 == ODESolver::rk4_solve integrator.cpp:86-98, looped by

@@ -144,6 +144,8 @@ public:
     Function getNumericJacobian() { return NumJacobian; }
     /** d f/d u (13x3): not exposed by the reference class, used by the sensitivity / collocation paths */
     Function getNumericControlJacobian() { return NumControlJacobian; }
+    /** Aero(x[13], u[3]) -> body-frame aerodynamic force Faero_b[3]   (kite.h:126, kite.cpp:224-234, :330) */
+    Function getAeroDynamicForces() { return AeroDynamics; }
 
     std::shared_ptr<KiteContext> context() const { return Ctx; }
     const KiteProperties& properties() const { return Props; }
@@ -174,6 +176,14 @@ private:
         };
         NumJacobian = Function("dyn_jacobian", ins, {169}, [jac](const DMVector& a) { return DMVector{jac(a, false)}; }, c);
         NumControlJacobian = Function("dyn_jacobian_u", ins, {39}, [jac](const DMVector& a) { return DMVector{jac(a, true)}; }, c);
+        AeroDynamics = Function("Aero", ins, {3}, [c, id](const DMVector& a) {
+            double* s = c->stage;
+            c->h2d(s, a[0].ptr(), 13); c->h2d(s + 13, a[1].ptr(), 3);
+            if (id) c->h2d(s + 16, a[2].ptr(), 21);
+            c->check(kite_aero_batch(c->ctx, 1, 1, s, s + 13, id ? s + 16 : nullptr, s + 64), "kite_aero_batch");
+            DM F(3, 1); c->d2h(F.ptr(), s + 64, 3);
+            return DMVector{F};
+        }, c);
         if (!id) {
             NumIntegrator = Function("RK4", {13, 3, 1}, {13}, [c](const DMVector& a) {
                 double* s = c->stage;
@@ -187,7 +197,7 @@ private:
     }
     KiteProperties Props;
     std::shared_ptr<KiteContext> Ctx;
-    Function NumDynamics, NumIntegrator, NumJacobian, NumControlJacobian;
+    Function NumDynamics, NumIntegrator, NumJacobian, NumControlJacobian, AeroDynamics;
 };
 
 /** RigidBodyKinematics (kite.h:153-173, kite.cpp:622-661).  The reference's integrator here is CVODES; the engine

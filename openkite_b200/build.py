@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libkite_b200.so")
+LIB_CASADI = os.path.join(HERE, "libkite_casadi.so")     # CasADi external-function shim (host C++, links LIB)
 UNITS = ["kite_capi", "launch_point", "launch_rollout_a", "launch_rollout_b", "launch_sens", "launch_ekf", "launch_colloc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
@@ -62,7 +63,25 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    build_casadi_shim(force or bool(todo))
     return LIB
+
+
+def build_casadi_shim(force=False):
+    """libkite_casadi.so: `dynamics`, `dyn_jacobian`, `Aero`, `RK4` in CasADi's external-function C convention
+    (csrc/kite_casadi.cpp, plain g++), on top of the B = 1 entry points of libkite_b200.so."""
+    src = os.path.join(CSRC, "kite_casadi.cpp")
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    newest = max([os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "kite_sparsity.h"))] +
+                 [os.path.getmtime(os.path.join(inc, "openkite", f)) for f in os.listdir(os.path.join(inc, "openkite"))])
+    if not force and os.path.exists(LIB_CASADI) and os.path.getmtime(LIB_CASADI) >= newest:
+        return LIB_CASADI
+    cmd = ["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-Wall", "-o", LIB_CASADI, src, "-L" + HERE, "-lkite_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("libkite_casadi.so failed:\n" + r.stdout + r.stderr)
+    return LIB_CASADI
 
 
 def build_variant(tag, extra_flags):

@@ -187,7 +187,7 @@ long long kite_launch_count(const kite_ctx* ctx) { return ctx ? ctx->launches : 
 
 // ---------------------------------------------------------------- pointwise ----------------------
 static int point_eval(kite_ctx* ctx, long B, long ld, const double* x, const double* u, const double* p, double* f,
-                      double* Jx, double* Ju, bool jac) {
+                      double* Jx, double* Ju, bool jac, double* fa = nullptr) {
     if (ctx && B == 0) return KITE_OK;
     if (!ctx || !x || B < 0 || ld < B) return fail(ctx, KITE_ERR_ARG, "point_eval: bad argument");
     const bool rigid = ctx->model_kind == KITE_MODEL_RIGID_BODY;
@@ -200,7 +200,7 @@ static int point_eval(kite_ctx* ctx, long B, long ld, const double* x, const dou
         if (Jx) CK(cudaMemset2DAsync(Jx, sizeof(double) * (size_t)ld, 0, sizeof(double) * (size_t)B, 169, ctx->stream));
         if (Ju) CK(cudaMemset2DAsync(Ju, sizeof(double) * (size_t)ld, 0, sizeof(double) * (size_t)B, 39, ctx->stream));
     }
-    PointArgs a{ctx->K, B, ld, x, u, p, f, Jx, Ju};
+    PointArgs a{ctx->K, B, ld, x, u, p, f, Jx, Ju, fa};
     launch_point_eval(a, rigid, p != nullptr, jac, ctx->stream);
     LAUNCH_CHECK("k_point_eval");
     return KITE_OK;
@@ -209,6 +209,26 @@ static int point_eval(kite_ctx* ctx, long B, long ld, const double* x, const dou
 int kite_rhs_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d, double* f_d) {
     if (!f_d) return fail(ctx, KITE_ERR_ARG, "kite_rhs_batch: f_d is null");
     return point_eval(ctx, B, ld, x_d, u_d, p_d, f_d, nullptr, nullptr, false);
+}
+int kite_jac_sparsity(int model_kind, int has_arm, int wrt_u, int* row_out, int* col_out) {
+    if (model_kind < 0 || model_kind > 2) return KITE_ERR_ARG;
+    const bool rigid = model_kind == KITE_MODEL_RIGID_BODY;
+    int n = 0;
+    const int ncol = wrt_u ? 3 : 13;
+    for (int j = 0; j < ncol; ++j)                   // CCS order: columns, rows ascending inside a column
+        for (int i = 0; i < 13; ++i) {
+            const bool nz = wrt_u ? (!rigid && ju_nz(i, j)) : (rigid ? jx_nz_rigid(i, j) : jx_nz(i, j, has_arm != 0));
+            if (!nz) continue;
+            if (row_out) row_out[n] = i;
+            if (col_out) col_out[n] = j;
+            ++n;
+        }
+    return n;
+}
+int kite_aero_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d, double* F_d) {
+    if (!F_d) return fail(ctx, KITE_ERR_ARG, "kite_aero_batch: F_d is null");
+    if (ctx && ctx->model_kind == KITE_MODEL_RIGID_BODY) return fail(ctx, KITE_ERR_STATE, "kite_aero_batch: kite models only");
+    return point_eval(ctx, B, ld, x_d, u_d, p_d, nullptr, nullptr, nullptr, false, F_d);
 }
 int kite_jac_batch(kite_ctx* ctx, long B, long ld, const double* x_d, const double* u_d, const double* p_d, double* Jx_d,
                    double* Ju_d) {

@@ -12,6 +12,7 @@
 #include <cuda_pipeline.h>
 
 #include "kite_model.cuh"
+#include "kite_sparsity.h"
 
 namespace kite {
 
@@ -19,17 +20,7 @@ namespace kite {
 // Structural non-zeros of [Jx | Ju], row-major slot numbering.  The 21 entries
 // that only exist with a tether arm (rows w_dot, cols r,q) get slots too but are only touched when
 // has_arm.  The slot tables of the kernels (SENS_TAB) are built from these predicates.
-__host__ __device__ constexpr bool jx_nz(int i, int j, bool arm) {
-    if (i < 3) return !((i == 0 && j == 3) || (i == 2 && j == 5));
-    if (i < 6) return (j < 6) || arm;
-    if (i < 9) return (j < 3) || (j >= 9);
-    return (j >= 3 && j < 6) || (j >= 9);
-}
 constexpr int JX_SLOTS = 125;
-__host__ __device__ constexpr bool ju_nz(int i, int j) {
-    return (i == 0 && j == 0) || (i == 0 && j == 1) || (i == 2 && j == 1) || (i == 4 && j == 1) ||
-           (i == 1 && j == 2) || (i == 3 && j == 2) || (i == 5 && j == 2);
-}
 constexpr int JAC_SLOTS = JX_SLOTS + 7;   // 132
 constexpr int JAC_SLOTS_NOARM = 111;      // 104 + 7 structural non-zeros of a zero-arm model (+ 21 with a tether arm)
 
@@ -38,6 +29,7 @@ struct DenseSink {
     double* jxp; double* jup; long ld;
     __device__ __forceinline__ void jx(int i, int j, double v) const { if (jxp) jxp[(long)(i * 13 + j) * ld] = v; }
     __device__ __forceinline__ void ju(int i, int j, double v) const { if (jup) jup[(long)(i * 3 + j) * ld] = v; }
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 __device__ __forceinline__ void load_coef(const KiteConsts& K, const double* __restrict__ p, long ld, long i, AeroCoef& A) {
@@ -62,6 +54,13 @@ struct PointArgs {
     long B, ld;
     const double* x; const double* u; const double* p;
     double* f; double* Jx; double* Ju;
+    double* fa;              // [3][ld] body-frame aerodynamic force (Function "Aero", kite.cpp:330) or null
+};
+struct AeroSink {           // RHS-only evaluation that also captures the aerodynamic force
+    double* fap; long ld;
+    __device__ __forceinline__ void jx(int, int, double) const {}
+    __device__ __forceinline__ void ju(int, int, double) const {}
+    __device__ __forceinline__ void aero(double fx, double fy, double fz) const { if (fap) { fap[0] = fx; fap[ld] = fy; fap[2 * ld] = fz; } }
 };
 
 template <bool RIGID, bool PERCOEF, bool JAC>
@@ -79,7 +78,7 @@ __global__ void __launch_bounds__(128) k_point_eval(const __grid_constant__ Poin
         DenseSink s{a.Jx ? a.Jx + i : nullptr, a.Ju ? a.Ju + i : nullptr, a.ld};
         model_eval<RIGID, true>(a.K, A, x, u, f, s);
     } else {
-        NoSink s;
+        AeroSink s{a.fa ? a.fa + i : nullptr, a.ld};
         model_eval<RIGID, false>(a.K, A, x, u, f, s);
     }
     if (a.f) {
@@ -381,6 +380,7 @@ struct StageSink {      // the warp's tile: compact slots of this lane's (unit, 
     double* base;
     __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 4] = v; }
     __device__ __forceinline__ void ju(int i, int j, double v) const { base[SENS_TAB.ju[i][j] * 4] = v; }
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 template <bool ARM, bool RIGID, bool TMA_OUT>
@@ -674,6 +674,7 @@ struct SmemSink {       // compact slots of this lane's filter in the warp's sha
     double* base;       // &Jt[lane / 4][0][lane % 4]
     __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 4] = v; }
     __device__ __forceinline__ void ju(int, int, double) const {}     // the EKF uses the state Jacobian only
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 // y[i] += sum_j J[i][j] v[j] for two vectors at once, J from the shared tile column of this lane's filter
@@ -829,6 +830,7 @@ struct Rep0Sink {       // compact state-Jacobian slots of this lane's filter; o
     bool on;
     __device__ __forceinline__ void jx(int i, int j, double v) const { if (on) base[SENS_TAB.jx[i][j] * 4] = v; }
     __device__ __forceinline__ void ju(int, int, double) const {}
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1122,6 +1124,7 @@ struct CollocSink {
     const double* sx; const double* isx; const double* isu;
     __device__ __forceinline__ void jx(int i, int j, double v) const { if (jxp) jxp[(long)(i * 15 + j) * ld] = sx[i] * v * isx[j]; }
     __device__ __forceinline__ void ju(int i, int j, double v) const { if (jup) jup[(long)(i * 4 + j) * ld] = sx[i] * v * isu[j]; }
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 // ---- compact node blocks: structural non-zeros only, in CCS (column-major) order ------------------------------------
@@ -1163,6 +1166,7 @@ struct CollocSparseSink {       // value of entry (i, j) of the node block goes 
         const int sl = (ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[i][15 + j];
         if (sl >= 0) jv[(long)sl * ld] = sx[i] * v * isu[j];
     }
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 // FMT 0: dense 15 x 15 / 15 x 4 node blocks (JX, JU);  1 / 2: structural non-zeros only (JV), without / with tether arm.

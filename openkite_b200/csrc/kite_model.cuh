@@ -112,6 +112,7 @@ __device__ __forceinline__ void attitude_matrix(double s, const double (&a)[3], 
 struct NoSink {
     __device__ __forceinline__ void jx(int, int, double) const {}
     __device__ __forceinline__ void ju(int, int, double) const {}
+    __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
 // =====================================================================================
@@ -195,6 +196,7 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     const double Fx = fma(cb, X1, -sa * Zde);
     const double Fy = fma(sb, X1, SF);
     const double Fz = fma(ca, Zde, Z1);
+    sink.aero(Fx, Fy, Fz);                                    // body-frame aerodynamic force: Function "Aero" (kite.cpp:330)
 
     // ---- attitude matrix M(q):  q (x) [0,y] (x) conj(q) = M y,   conj(q) (x) [0,y] (x) q = M^T y ----
     double M[3][3], nq;

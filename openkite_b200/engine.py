@@ -94,6 +94,7 @@ def load_library():
     L.kite_launch_count.argtypes = [vp]; L.kite_launch_count.restype = C.c_longlong
     L.kite_rhs_batch.argtypes = [vp, lg, lg, dp, dp, dp, dp]
     L.kite_jac_batch.argtypes = [vp, lg, lg, dp, dp, dp, dp, dp]
+    L.kite_aero_batch.argtypes = [vp, lg, lg, dp, dp, dp, dp]
     L.kite_rk4_rollout.argtypes = [vp, lg, lg, lg, db, dp, dp, ip, dp, dp, dp, lg, dp, dp, dp, lg]
     L.kite_rk4_rollout_host.argtypes = [vp, lg, lg, db, dp, dp, ip, dp, dp, dp, dp, dp]
     L.kite_synth_inputs.argtypes = [vp, lg, lg, lg, lg, dp, dp]
@@ -196,6 +197,14 @@ class Engine:
         f = self.empty(13, B)
         self._ck(self.L.kite_rhs_batch(self.ctx, B, B, _ptr(x), _ptr(u), _ptr(p), _ptr(f)))
         return f
+
+    def aero(self, x, u, p=None):
+        """Body-frame aerodynamic force [3, B] (Function "Aero", kite.cpp:330)."""
+        self._use_torch_stream()
+        B = x.shape[1]
+        F = self.empty(3, B)
+        self._ck(self.L.kite_aero_batch(self.ctx, B, B, _ptr(x), _ptr(u), _ptr(p), _ptr(F)))
+        return F
 
     def jac(self, x, u, p=None):
         self._use_torch_stream()

@@ -173,7 +173,8 @@ inline void nominal_id_params(const Params& P, double p[21]) {
 //   kind == KITE_ID  : kite.cpp:448-573 (no regularisers, 21 coefficients from `p`)
 // ------------------------------------------------------------------------------------
 template <class T>
-void kite_rhs(const Params& P, ModelKind kind, const T x[13], const T u[3], const T* p /*21 or null*/, T f[13]) {
+void kite_rhs(const Params& P, ModelKind kind, const T x[13], const T u[3], const T* p /*21 or null*/, T f[13],
+              T* faero_out = nullptr /* 3: Faero_b, the output of Function "Aero" (kite.cpp:330) */) {
     const double g = 9.80665;     // kite.cpp:93
     const double ro = 1.2985;     // kite.cpp:94
     const double pi = 3.14159265358979323846;   // casadi::pi
@@ -239,6 +240,7 @@ void kite_rhs(const Params& P, ModelKind kind, const T x[13], const T u[3], cons
     Faero_b[0] = Faero_b[0] + qFdE[1];                                                // :234
     Faero_b[1] = Faero_b[1] + qFdE[2] + SF;
     Faero_b[2] = Faero_b[2] + qFdE[3];
+    if (faero_out) { faero_out[0] = Faero_b[0]; faero_out[1] = Faero_b[1]; faero_out[2] = Faero_b[2]; }
 
     T q_inv[4]; quat_inverse(q, q_inv);
     T gq[4] = {T(0.0), T(0.0), T(0.0), T(g)};

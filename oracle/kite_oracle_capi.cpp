@@ -62,6 +62,13 @@ void orc_rhs(const double* prm, int kind, long n, const double* x, const double*
         model_rhs<double>(P, (ModelKind)kind, x + 13 * i, u + 3 * i, p ? p + 21 * i : nullptr, f + 13 * i);
 }
 
+// Function "Aero"(x,u) -> Faero_b (kite.cpp:330); kind KITE or KITE_ID
+void orc_aero(const double* prm, int kind, long n, const double* x, const double* u, const double* p, double* F) {
+    const Params& P = as_params(prm);
+    double f[13];
+    for (long i = 0; i < n; ++i) kite_rhs<double>(P, (ModelKind)kind, x + 13 * i, u + 3 * i, p ? p + 21 * i : nullptr, f, F + 3 * i);
+}
+
 void orc_jac(const double* prm, int kind, long n, const double* x, const double* u, const double* p, double* Jx, double* Ju) {
     const Params& P = as_params(prm);
     for (long i = 0; i < n; ++i)

@@ -84,6 +84,16 @@ class Oracle:
         self.lib.orc_rhs(_p(self.prm), C.c_int(kind), C.c_long(n), _p(x), _p(u), _p(p), _p(f))
         return f
 
+    def aero(self, x, u, p=None, kind=KITE):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)
+        n = x.shape[0]
+        F = np.empty((n, 3))
+        if p is not None:
+            p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
+        self.lib.orc_aero(_p(self.prm), C.c_int(kind), C.c_long(n), _p(x), _p(u), _p(p), _p(F))
+        return F
+
     def jac(self, x, u, p=None, kind=KITE):
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)

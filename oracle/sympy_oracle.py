@@ -113,6 +113,7 @@ def build_rhs(cfg, kind="kite"):
     qq1 = sum(qi * qi for qi in q) - 1
     q_dot = [sp.Rational(1, 2) * qw[i] + sp.Rational(1, 2) * lam * q[i] * qq1 for i in range(4)]
     f = [*v_dot, *list(w_dot), *vi, *q_dot]
+    build_rhs.last_aero = list(Faero)            # Function "Aero" (kite.cpp:330): body-frame aerodynamic force
     return x, u, p, f
 
 
@@ -126,6 +127,7 @@ class SymModel:
         fm = sp.Matrix(f)
         args = [*x, *u, *p]
         self._f = sp.lambdify(args, list(fm), modules="mpmath", cse=True)
+        self._aero = sp.lambdify(args, list(getattr(build_rhs, "last_aero", [0, 0, 0])), modules="mpmath", cse=True) if kind != "rigid_body" else None
         Jx = fm.jacobian(sp.Matrix(x))
         Ju = fm.jacobian(sp.Matrix(u))
         self._J = sp.lambdify(args, [list(Jx), list(Ju)], modules="mpmath", cse=True)
@@ -133,6 +135,10 @@ class SymModel:
     def f(self, x, u, p=()):
         a = [mp.mpf(t) for t in (*x, *u, *p)]
         return [mp.mpf(t) for t in self._f(*a)]
+
+    def aero(self, x, u, p=()):
+        a = [mp.mpf(t) for t in (*x, *u, *p)]
+        return [mp.mpf(t) for t in self._aero(*a)]
 
     def jac(self, x, u, p=()):
         a = [mp.mpf(t) for t in (*x, *u, *p)]

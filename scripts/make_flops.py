@@ -101,7 +101,7 @@ inline real_t __dmul_rn(real_t a, real_t b) { return a * b; }
 #include "kite_model_counting.cuh"
 #include <cstdio>
 using namespace kite;
-struct NullSink { int nx = 0, nu = 0; void jx(int, int, real_t) { ++nx; } void ju(int, int, real_t) { ++nu; } };
+struct NullSink { int nx = 0, nu = 0; void jx(int, int, real_t) { ++nx; } void ju(int, int, real_t) { ++nu; } void aero(real_t, real_t, real_t) {} };
 static void report(const char* name, int nx = 0, int nu = 0) {
     Tally& t = tally();
     std::printf("%s add=%ld mul=%ld fma=%ld div=%ld mufu=%ld other=%ld nx=%d nu=%d\n", name, t.add, t.mul, t.fma, t.div, t.mufu, t.other, nx, nu);

@@ -69,7 +69,26 @@ SCALE_U = [1 / 0.15, 1 / 0.2618, 1 / 0.2618, 1 / 5.0]
 EKF_SIG = [0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.1, 0.1, 0.01, 0.05, 0.05, 0.05]   # kiteEKF.cpp:6-11
 
 
+def add_aero_only():
+    """Adds the output of Function "Aero" (kite.cpp:330) to the existing rhs cases without regenerating the rest."""
+    path = os.path.join(ROOT, "tests", "golden", "golden.json")
+    out = json.load(open(path))
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "data", "umx_radian.yaml")))
+    cfg.setdefault("tether", {})
+    kite = so.SymModel(cfg, "kite")
+    for name, c in out["cases"]["rhs"].items():
+        c["aero"] = fl(kite.aero(c["x"], c["u"]))
+    kid = so.SymModel(cfg, "kite_id")
+    for name, c in out["cases"]["rhs_id"].items():
+        c["aero"] = fl(kid.aero(c["x"], c["u"], c["p"]))
+    with open(path, "w") as fh:
+        json.dump(out, fh, indent=0)
+    print("aero added to %d + %d cases" % (len(out["cases"]["rhs"]), len(out["cases"]["rhs_id"])))
+
+
 def main():
+    if "--aero-only" in sys.argv:
+        return add_aero_only()
     t0 = time.time()
     cfg = yaml.safe_load(open(os.path.join(ROOT, "data", "umx_radian.yaml")))
     cfg.setdefault("tether", {})
@@ -93,7 +112,7 @@ def main():
     for name, (x, u) in pts.items():
         f = kite.f(x, u)
         Jx, Ju = kite.jac(x, u)
-        C["rhs"][name] = dict(kind="kite", x=x, u=u, f=fl(f), Jx=fl(Jx), Ju=fl(Ju))
+        C["rhs"][name] = dict(kind="kite", x=x, u=u, f=fl(f), Jx=fl(Jx), Ju=fl(Ju), aero=fl(kite.aero(x, u)))
 
     # ---- RK4 single steps with sensitivities -------------------------------------------------
     C["rk4_step"] = {}

@@ -93,6 +93,7 @@ int main(int argc, char** argv) {
     std::vector<double> f_ref = read_vec(gf, "rhs_model_test");
     CHECK(close_vec(ode(DMVector{init_state, control})[0], f_ref, 1e-9));
     std::vector<double> jx_ref = read_vec(gf, "jx_model_test");         // row-major 13x13
+    CHECK(close_vec(kite.getAeroDynamicForces()(DMVector{init_state, control})[0], read_vec(gf, "aero"), 1e-9));     // Function "Aero", kite.cpp:330
     DM Jx = kite.getNumericJacobian()(DMVector{init_state, control})[0];
     { bool ok = true; for (int i = 0; i < 13; ++i) for (int j = 0; j < 13; ++j) ok = ok && std::fabs(Jx(i, j) - jx_ref[i * 13 + j]) <= 1e-9 * std::fmax(1.0, std::fabs(jx_ref[i * 13 + j])); CHECK(ok); }
     // the caller's time loop around solve(): 10 s at 1 ms (BASELINE.json configs[0], simulator.cpp:43-51)

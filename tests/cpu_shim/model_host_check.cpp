@@ -11,6 +11,7 @@ struct DenseSink {
     double* Jx; double* Ju;
     void jx(int i, int j, double v) { Jx[i * 13 + j] = v; }
     void ju(int i, int j, double v) { Ju[i * 3 + j] = v; }
+    void aero(double, double, double) {}
 };
 
 extern "C" {

@@ -60,6 +60,21 @@ def test_rhs_jac_golden(eng, golden):
         assert_close(Ju[i], c["Ju"], RTOL, what=f"Ju[{n}]")
 
 
+def test_aero_function_golden_and_batch(eng, okb, params, oracle, golden):
+    """kite_aero_batch = Function "Aero" (kite.cpp:330): goldens, a batch against the oracle, and the id variant."""
+    for name, c in golden["rhs"].items():
+        F = eng.aero(soa([c["x"]]), soa([c["u"]]))
+        assert_close(aos(F)[0], c["aero"], RTOL, what=f"aero[{name}]")
+    B = 1031
+    x = oracle.synth_x0(7, B); u = oracle.synth_controls(7, B, 1)[:, 0, :]
+    assert_close(aos(eng.aero(soa(x), soa(u))), oracle.aero(x, u), RTOL, what="aero batch")
+    e = okb.Engine(params, okb.KITE_ID)
+    for name, c in golden["rhs_id"].items():
+        F = e.aero(soa([c["x"]]), soa([c["u"]]), soa([c["p"]]))
+        assert_close(aos(F)[0], c["aero"], RTOL, what=f"aero id[{name}]")
+    e.close()
+
+
 def test_config1_rollout_golden(eng, golden, okb):
     """BASELINE.json configs[0]: umx_radian, 10 s at dt = 1 ms, one trajectory (B = 1 semantics)."""
     c = golden["rollout_config1"]

@@ -35,7 +35,7 @@ def test_host_api_on_gpu(host_bin, yaml_path, golden, oracle, tmp_path):
         lines.append("%s %d %s" % (tag, v.size, " ".join(repr(float(t)) for t in v)))
 
     c = golden["rhs"]["model_test"]
-    put("rhs_model_test", c["f"]); put("jx_model_test", c["Jx"])
+    put("rhs_model_test", c["f"]); put("jx_model_test", c["Jx"]); put("aero", c["aero"])
     r = golden["rollout_config1"]["states_after"]
     put("config1_after_1", r["1"]); put("config1_after_1000", r["1000"])
     e = golden["ekf_predict"]

@@ -18,6 +18,18 @@ def test_rhs_and_jacobians(oracle, golden):
         assert_close(Ju[0], c["Ju"], TOL, what=f"Ju[{name}]")
 
 
+def test_aero_function(oracle, golden):
+    """Function "Aero"(x, u) -> Faero_b (kite.cpp:224-234, :330; KiteDynamics::getAeroDynamicForces, kite.h:126)."""
+    for name, c in golden["rhs"].items():
+        assert_close(oracle.aero(c["x"], c["u"])[0], c["aero"], TOL, what=f"aero[{name}]")
+    for name, c in golden["rhs_id"].items():
+        assert_close(oracle.aero(c["x"], c["u"], c["p"], kind=KITE_ID)[0], c["aero"], TOL, what=f"aero id[{name}]")
+    # no thrust, tether or gravity in it: the force is invariant under T, position and attitude
+    c = golden["rhs"]["model_test"]
+    x = np.array(c["x"]); x2 = x.copy(); x2[6:9] += 1.0; x2[9:13] = [1.0, 0.0, 0.0, 0.0]
+    assert np.array_equal(oracle.aero(x, [0.1, 0.02, 0.01]), oracle.aero(x2, [0.3, 0.02, 0.01]))
+
+
 def test_jacobian_sparsity_matches_survey(oracle, golden):
     # SURVEY.md Appendix A: 104 + 7 structural non-zeros when the tether arm is zero
     c = golden["rhs"]["model_test_u"]
