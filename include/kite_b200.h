@@ -47,6 +47,13 @@ typedef enum kite_status {
     KITE_ERR_STATE = -4    /* call not valid for this context (e.g. model kind) */
 } kite_status;
 
+/* Per-unit status flags (int32, OR-ed): what the rollout's status_d and the buffer of kite_set_status_buffer carry. */
+typedef enum kite_status_flag {
+    KITE_FLAG_NONFINITE = 1,     /* a result of this unit is NaN / Inf */
+    KITE_FLAG_LOW_AIRSPEED = 2,  /* evaluated at |v|^2 < 1e-12: the aerodynamic angles are regulariser-dominated (kite.cpp:200-201) */
+    KITE_FLAG_ZERO_TETHER = 4    /* evaluated at |r|^2 < 1e-18: the tether direction r/|r| is undefined (kite.cpp:247-258) */
+} kite_status_flag;
+
 /* Which right-hand side the context evaluates. */
 typedef enum kite_model_kind {
     KITE_MODEL_KITE = 0,       /* KiteDynamics(props, algo)        kite.cpp:90-363  (1e-4 regularisers) */
@@ -82,6 +89,12 @@ int kite_destroy(kite_ctx* ctx);
  * A new context launches on its own non-blocking stream; kite_reset_stream returns to it. */
 int kite_set_stream(kite_ctx* ctx, void* cuda_stream);
 int kite_reset_stream(kite_ctx* ctx);
+/* Per-unit status flags next to the results.  While a buffer is set (status_d: DEVICE int32 [ld]; NULL
+ * switches it off), kite_rk4_sens_step / _rollout, kite_ekf_predict_batch / _update_batch and kite_colloc_eval[_sparse]
+ * write one kite_status_flag word per unit: non-finite results and the V -> 0 / |r| -> 0 singularities of the state(s) the
+ * model was evaluated at (pre-step state for the integrators, OR over the steps of a rollout and over the nodes of a
+ * scenario).  The reference has no such channel: CasADi returns NaN silently.  kite_rk4_rollout has its own status_d. */
+int kite_set_status_buffer(kite_ctx* ctx, int32_t* status_d);
 int kite_synchronize(kite_ctx* ctx);
 const char* kite_last_error(const kite_ctx* ctx);
 const char* kite_version(void);

@@ -84,6 +84,7 @@ struct kite_ctx {
     DevBuf counters;                     // dynamic work counters of the persistent kernels
     nccl_comm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    int32_t* status_out = nullptr;       // kite_set_status_buffer: per-unit flags of the sensitivity / EKF / collocation calls
 };
 
 static int fail(kite_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
@@ -138,6 +139,11 @@ int kite_destroy(kite_ctx* ctx) {
 int kite_set_stream(kite_ctx* ctx, void* s) {
     if (!ctx) return KITE_ERR_ARG;
     ctx->stream = (cudaStream_t)s;      // NULL = the CUDA default stream
+    return KITE_OK;
+}
+int kite_set_status_buffer(kite_ctx* ctx, int32_t* status_d) {
+    if (!ctx) return KITE_ERR_ARG;
+    ctx->status_out = status_d;
     return KITE_OK;
 }
 int kite_reset_stream(kite_ctx* ctx) {
@@ -405,6 +411,8 @@ static int sens_impl(kite_ctx* ctx, long B, long ld, long N, double h, const dou
     a.Sw = (double*)work; a.next_group = (unsigned long long*)ctx->counters.ptr;
     a.done = (int*)((char*)work + sens_state_bytes(B));
     if (N > 1) CK(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)((B + 31) / 32), ctx->stream));
+    a.status = ctx->status_out;
+    if (a.status) CK(cudaMemsetAsync(a.status, 0, sizeof(int32_t) * (size_t)B, ctx->stream));      // the kernel ORs flags in
     // [Phi | Gamma] leave through TMA tensor stores when the output layout allows it (16-byte aligned base and pitch:
     // an even ld; an even B); KITE_SENS_DIRECT_STORES=1 forces the direct-store kernel (developer comparison switch)
     static const bool direct = getenv("KITE_SENS_DIRECT_STORES") && getenv("KITE_SENS_DIRECT_STORES")[0] == '1';
@@ -454,7 +462,7 @@ static int colloc_eval_impl(kite_ctx* ctx, long B, long ld, int M, const double*
     for (int i = 0; i < 15; ++i) { a.sx[i] = sx_h[i]; a.isx[i] = 1.0 / sx_h[i]; }
     for (int i = 0; i < 4; ++i) { a.su[i] = su_h[i]; a.isu[i] = 1.0 / su_h[i]; }
     a.compD = (const double*)ctx->small.ptr;
-    a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d;
+    a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d; a.status = ctx->status_out;
     launch_colloc_eval(a, p_d != nullptr, sparse ? (ctx->K.has_arm ? 2 : 1) : 0, ctx->stream);
     LAUNCH_CHECK("k_colloc_eval");
     return KITE_OK;
@@ -538,7 +546,7 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemsetAsync((char*)ctx->counters.ptr + 8, 0, 8, ctx->stream));
     EkfArgs a{ctx->K, B, ld, dt, dt / 6.0, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
-              (unsigned long long*)((char*)ctx->counters.ptr + 8)};
+              (unsigned long long*)((char*)ctx->counters.ptr + 8), ctx->status_out};
     if (ctx->ekf_lines.reserve(ekf_predict_scratch_bytes())) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, (double*)ctx->ekf_lines.ptr, ctx->stream);
     LAUNCH_CHECK("k_ekf_predict");
@@ -553,7 +561,7 @@ int kite_ekf_update_batch(kite_ctx* ctx, long B, long ld, const double* z_d, con
     if (ctx->small.reserve(4096)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     double* Vd = (double*)ctx->small.ptr + 256;     // keep clear of W staging
     CK(cudaMemcpyAsync(Vd, V_h, sizeof(double) * 49, cudaMemcpyHostToDevice, ctx->stream));
-    EkfUpdArgs a{B, ld, z_d, P_d, x_d, Vd};          // in place: no staging copy of the covariance
+    EkfUpdArgs a{B, ld, z_d, P_d, x_d, Vd, ctx->status_out};          // in place: no staging copy of the covariance
     launch_ekf_update(a, ctx->stream);
     LAUNCH_CHECK("k_ekf_update");
     return KITE_OK;

@@ -46,6 +46,17 @@ __device__ __forceinline__ bool all_finite13(const double (&x)[13]) {
     return s == 0.0;
 }
 
+// Per-unit status flags (include/kite_b200.h, kite_status_flag) of a state the kite model is evaluated at: the airspeed
+// and tether-length singularities of the RHS.  Callers OR in KITE_FLAG_NONFINITE for their results.
+constexpr int FLAG_NONFINITE = 1, FLAG_LOW_AIRSPEED = 2, FLAG_ZERO_TETHER = 4;
+template <bool RIGID>
+__device__ __forceinline__ int singularity_flags(const double (&x)[13]) {
+    if constexpr (RIGID) return 0;                  // the rigid-body kinematics have neither term
+    const double V2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double d2 = fma(x[6], x[6], fma(x[7], x[7], x[8] * x[8]));
+    return (V2 < 1e-12 ? FLAG_LOW_AIRSPEED : 0) | (d2 < 1e-18 ? FLAG_ZERO_TETHER : 0);
+}
+
 // ================================================================================================
 // rhs_batch / jac_batch : pointwise evaluators (kite.cpp:324, :327-328)
 // ================================================================================================
@@ -298,6 +309,7 @@ struct SensArgs {
     double* Sw;     // scratch: [resident warp][4 stages][16 = x(13) | u(3)][32 units]
     unsigned long long* next_group;   // device counter (zeroed before the launch): work items are handed out dynamically
     int* done;      // [groups] steps finished per group (zeroed before the launch; only used when N > 1)
+    int32_t* status;  // [ld] per-unit flags, OR over the steps (zeroed before the launch), or null
 };
 
 
@@ -496,7 +508,11 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
             }
             if (unit < a.B) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcg(xout + (long)c * a.ld + unit, fma(h6, acc[c], x[c]));
+                for (int c = 0; c < 13; ++c) { acc[c] = fma(h6, acc[c], x[c]); __stcg(xout + (long)c * a.ld + unit, acc[c]); }
+                if (a.status) {                         // (warp-uniform) flags of this step, OR-ed into the unit's word
+                    const int fl = singularity_flags<RIGID>(x) | (all_finite13(acc) ? 0 : FLAG_NONFINITE);
+                    if (fl) atomicOr(a.status + unit, fl);
+                }
             }
             if (a.N > 1) {                              // publish: step ks of this group is done (release after every lane's stores)
                 __threadfence();
@@ -653,6 +669,7 @@ struct EkfArgs {
     double* xn; double* Pn;
     const double* W;         // device [169]
     unsigned long long* next_group;   // device counter (zeroed before the launch): groups are handed out dynamically
+    int32_t* status;         // [ld] per-filter flags or null
 };
 template <bool ARM> struct EfCfg {
     // state-Jacobian slots only (the EKF needs no Ju), numbered as in the sensitivity kernel (repeated +-q/2 entries share
@@ -729,7 +746,6 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
     };
     for (long g = claim_group(); g < ngroups; g = claim_group()) {
         double pn0[13], pn1[13];
-        load_rows(g, 0, pn0, pn1);                  // first pass's rows of P land behind phase A
         // ---------------- phase A: lane = filter ------------------------------------------------------------
         {
             const long unit = g * 32 + lane;
@@ -743,13 +759,17 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
                 SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
                 model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
             }
+            const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
             rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+                if (a.status) a.status[unit] = pre | (all_finite13(x) ? 0 : FLAG_NONFINITE);
             }
         }
         __syncwarp();
+        // (the first pass's rows are fetched here, not behind phase A: 52 more live registers across the Jacobian code spilled)
+        load_rows(g, 0, pn0, pn1);
         // ---------------- phase B: 8 lanes = filter, 4 filters per pass -------------------------------------
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
@@ -915,10 +935,12 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             for (int c = 0; c < 13; ++c) __stcg(Xw + c * 32 + lane, x[c]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) __stcg(Xw + (13 + c) * 32 + lane, u[c]);
+            const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
             rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+                if (a.status) a.status[unit] = pre | (all_finite13(x) ? 0 : FLAG_NONFINITE);
             }
         }
         __syncwarp();
@@ -1019,6 +1041,7 @@ struct EkfUpdArgs {
     long B, ld;
     const double* z; double* P; double* x;
     const double* V;         // device [49]
+    int32_t* status;         // [ld] per-filter flag (non-finite updated state: singular innovation covariance) or null
 };
 constexpr int EKFU_BLOCK = 128;
 template <int DUMMY = 0>
@@ -1073,7 +1096,8 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
 #pragma unroll
         for (int r = 0; r < 13; ++r) xv[r] = a.x[(long)r * ld + i];
 #pragma unroll
-        for (int r = 0; r < 13; ++r) a.x[(long)r * ld + i] = xv[r] + Ks[(91 + r) * EKFU_BLOCK];
+        for (int r = 0; r < 13; ++r) { xv[r] += Ks[(91 + r) * EKFU_BLOCK]; a.x[(long)r * ld + i] = xv[r]; }
+        if (a.status) a.status[i] = all_finite13(xv) ? 0 : FLAG_NONFINITE;
     }
     // P[:, c] <- P[:, c] - K (H P)[:, c], column by column; column c + 1 is loaded before column c is stored
     double hp[7], pv[13], hq[7], pq[13];
@@ -1117,6 +1141,7 @@ struct CollocArgs {
     const double* compD;     // device [M][M]
     const double* z; const double* p;
     double* G; double* JX; double* JU; double* gnorm;
+    int32_t* status;         // [ld] per-scenario flags, OR over the nodes, or null
 };
 
 struct CollocSink {
@@ -1173,6 +1198,8 @@ struct CollocSparseSink {       // value of entry (i, j) of the node block goes 
 template <bool PERCOEF, int NPB, int FMT>
 __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant__ CollocArgs a) {
     __shared__ double red[NPB][32];                // partial ||G||^2 per node row of the block
+    __shared__ int redf[NPB][32];                  // flags per node row of the block
+    int flags = 0;
     // per-scenario aero coefficients live in shared memory (one 21-double record per thread, re-read at every use): held in
     // registers they pushed the Jacobian code over the 255-register limit (136 B / 184 B of spills in round 1)
     __shared__ AeroCoef coef_sh[PERCOEF ? 32 * NPB : 1];
@@ -1198,6 +1225,7 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 3; ++c) u[c] = a.isu[c] * __ldg(zu + (long)c * a.ld);
             const double u3 = a.isu[3] * __ldg(zu + 3L * a.ld);
+            flags |= singularity_flags<false>(x);
             if constexpr (FMT == 0) {
                 CollocSink sink{a.JX ? a.JX + (long)(k * 225) * a.ld + s : nullptr,
                                 a.JU ? a.JU + (long)(k * 60) * a.ld + s : nullptr, a.ld, a.sx, a.isx, a.isu};
@@ -1261,14 +1289,17 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             }
         }
     }
-    if (a.gnorm) {
+    if (a.gnorm || a.status) {
         red[ky][lane] = g2;
+        redf[ky][lane] = flags;
         __syncthreads();
         if (ky == 0 && s < a.B) {
             double t = 0.0;
+            int fl = 0;
 #pragma unroll
-            for (int l = 0; l < NPB; ++l) t += red[l][lane];
-            a.gnorm[s] = t;
+            for (int l = 0; l < NPB; ++l) { t += red[l][lane]; fl |= redf[l][lane]; }
+            if (a.gnorm) a.gnorm[s] = t;
+            if (a.status) a.status[s] = fl | ((t * 0.0 == 0.0) ? 0 : FLAG_NONFINITE);     // a non-finite G poisons ||G||^2
         }
     }
 }

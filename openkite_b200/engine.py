@@ -89,6 +89,7 @@ def load_library():
     L.kite_set_stream.argtypes = [vp, vp]
     L.kite_synchronize.argtypes = [vp]
     L.kite_reset_stream.argtypes = [vp]
+    L.kite_set_status_buffer.argtypes = [vp, vp]
     L.kite_last_error.argtypes = [vp]; L.kite_last_error.restype = C.c_char_p
     L.kite_version.restype = C.c_char_p
     L.kite_launch_count.argtypes = [vp]; L.kite_launch_count.restype = C.c_longlong
@@ -181,6 +182,12 @@ class Engine:
         if self._work is None or self._work.numel() * 8 < nbytes:
             self._work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
         return self._work
+
+    def set_status_buffer(self, t):
+        """int32 CUDA tensor [B] (or None): per-unit kite_status_flag words of the sensitivity / EKF / collocation calls."""
+        assert t is None or (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous())
+        self._status = t
+        self._ck(self.L.kite_set_status_buffer(self.ctx, _ptr(t)))
 
     @property
     def launch_count(self):

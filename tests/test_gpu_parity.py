@@ -574,6 +574,65 @@ def test_colloc_sparse_blocks_match_dense(okb, params, oracle, golden):
         e.close()
 
 
+def test_status_flags_next_to_results(eng, okb, oracle, golden):
+    """kite_set_status_buffer: per-unit flags of the sensitivity / EKF / collocation calls: clean
+    inputs give 0; planted V -> 0, |r| -> 0 and NaN units are flagged, and only those."""
+    from openkite_b200.collocation import comp_diff_matrix
+    B = 200
+    x = oracle.synth_x0(11, B); u = oracle.synth_controls(11, B, 2)
+    x[3, 0:3] = 0.0                     # unit 3: no airspeed
+    x[5, 6:9] = 0.0                     # unit 5: at the tether anchor
+    x[7, 4] = np.nan                    # unit 7: poisoned
+    xd, ud = soa(x), soa(u[:, 0, :])
+    st = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    eng.set_status_buffer(st)
+    try:
+        eng.sens_step(xd, ud, 0.01)
+        torch.cuda.synchronize()
+        f = st.cpu().numpy()
+        assert f[3] & 2 and f[5] & 4 and f[7] & 1
+        clean = np.ones(B, bool); clean[[3, 5, 7]] = False
+        assert not f[clean].any()
+        # rollout: flags OR over the steps (the NaN unit stays flagged, step 2 of the V = 0 unit is clean but the flag stays)
+        st.fill_(-1)
+        eng.sens_rollout(xd, torch.from_numpy(np.ascontiguousarray(u.transpose(1, 2, 0))).cuda(), 0.01)
+        torch.cuda.synchronize()
+        f = st.cpu().numpy()
+        assert f[3] & 2 and f[5] & 4 and f[7] & 1 and not f[clean].any()
+        W, V = oracle.ekf_defaults()
+        P = torch.from_numpy((10 * W).reshape(169, 1)).cuda().expand(169, B).contiguous()
+        st.fill_(-1)
+        xn, Pn = eng.ekf_predict(xd, ud, 0.0084, P, W)
+        torch.cuda.synchronize()
+        f = st.cpu().numpy()
+        assert f[3] & 2 and f[5] & 4 and f[7] & 1 and not f[clean].any()
+        st.fill_(-1)
+        eng.ekf_update(xd[6:13].contiguous(), V, xn, Pn)
+        torch.cuda.synchronize()
+        f = st.cpu().numpy()
+        assert f[7] == 1 and not f[clean].any()
+        c = golden["colloc_nmpc_P5_S2_scaled"]
+        z = np.tile(np.array(c["z"])[None, :], (B, 1))
+        z[9, 3 * 15 + 0:3 * 15 + 3] = 0.0          # scenario 9, node 3: v = 0
+        z[12, 7 * 15 + 2] = np.inf
+        st.fill_(-1)
+        eng.colloc_eval(soa(z), 11, comp_diff_matrix(5, 2), 0.25, c["sx"], c["su"])
+        torch.cuda.synchronize()
+        f = st.cpu().numpy()
+        ok = np.ones(B, bool); ok[[9, 12]] = False
+        assert f[9] & 2 and f[12] & 1 and not f[ok].any()
+        st.fill_(-1)
+        eng.colloc_eval_sparse(soa(z), 11, comp_diff_matrix(5, 2), 0.25, c["sx"], c["su"])
+        torch.cuda.synchronize()
+        assert np.array_equal(st.cpu().numpy(), f)
+    finally:
+        eng.set_status_buffer(None)
+    st.fill_(-1)
+    eng.sens_step(xd, ud, 0.01)                     # buffer switched off: untouched
+    torch.cuda.synchronize()
+    assert int((st != -1).sum()) == 0
+
+
 def test_ekf_predict_vs_oracle_batch(eng, oracle):
     B, dt = 515, 0.0084
     x = oracle.synth_x0(0, B); u = oracle.synth_controls(0, B, 1)[:, 0, :]
