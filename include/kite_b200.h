@@ -257,7 +257,8 @@ int kite_comm_destroy(kite_ctx* ctx);
 int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out);
 /* Accuracy self-test of the engine's lean special functions on the device (MUFU seed + refinement):
  * out[i] = f(x[i]) with which = 0: 1/x, 1: 1/sqrt(x), 2: asin(x) for |x| <= 0.7072 (polynomial core),
- * 3: 1/(1+exp(-x)), 4: asin(x) for |x| <= 1 through the (sin, cos) pair form the model uses. */
+ * 3: 1/(1+exp(-x)), 4: asin(x) for |x| <= 1 through the (sin, cos) pair form the model uses,
+ * 5 / 6: the table-driven forms of 4 / 3 used by the kernels with per-trajectory coefficients (identification sweeps). */
 int kite_math_selftest(kite_ctx* ctx, long n, const double* x_d, double* out_d, int which);
 
 #ifdef __cplusplus

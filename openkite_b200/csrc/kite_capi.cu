@@ -603,7 +603,7 @@ int kite_comm_destroy(kite_ctx* ctx) {
 
 // ---------------------------------------------------------------- diagnostics ---------------------
 int kite_math_selftest(kite_ctx* ctx, long n, const double* x_d, double* out_d, int which) {
-    if (!ctx || n < 0 || !x_d || !out_d || which < 0 || which > 4) return fail(ctx, KITE_ERR_ARG, "kite_math_selftest: bad argument");
+    if (!ctx || n < 0 || !x_d || !out_d || which < 0 || which > 6) return fail(ctx, KITE_ERR_ARG, "kite_math_selftest: bad argument");
     if (n == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
     launch_math_selftest(x_d, out_d, n, which, ctx->stream);

@@ -360,13 +360,19 @@ constexpr size_t SF_SMEM_MAX = 227 * 1024;
 constexpr long SF_SCRATCH_PER_WARP = 4L * 16 * 32;      // doubles: [stage][x(13) | u(3)][32 units]
 template <bool ARM> struct SfCfg {
     static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM;    // slots a stage Jacobian occupies
-    static constexpr int TILE = NS * 4;                               // doubles per tile: [slot][4 units]
-    // tile stride: + one zero row (target of the gather's structural zeros), and == 4 (mod 16) doubles so that the 8
-    // four-lane groups (stage, pass) of a warp store land in distinct bank octets (conflict free, 2 wavefronts per STS.64)
-    static constexpr int TILE_S = TILE + 4 + ((4 - (TILE + 4) % 16) + 16) % 16;
-    // a warp's tiles are laid out [pass][stage]; the pass stride is == 8 (mod 16) doubles so that the four (stage, pass)
-    // groups of a half-warp store still land in distinct bank octets
-    static constexpr int PASS_S = 4 * TILE_S + 8;
+    // A stage tile holds the compact Jacobians of 4 units as two HALF tiles [slot][2 units] (units 0,1 | units 2,3), each
+    // with one extra "zero" slot (the target of the gather's structural zeros; step 2 never writes there).  Bank layout
+    // (16-byte groups, 8 per 128-byte wavefront): the half, stage and pass strides are == h, s, p (mod 8) groups with all
+    // eight subset sums of {h, s, p} distinct, so that
+    //   * the 16 lanes of a half-warp store of step 2 (2 stages x 2 passes x 2 halves x 2 units) fill one wavefront,
+    //   * a phase-B broadcast load (4 units = 2 groups) is one wavefront, and
+    //   * the stage-1 gather, where the 8 lanes of a unit read 8 (mostly consecutive) slots, sees 8 x 16 contiguous bytes per
+    //     half-warp instead of 16 of every 32 bytes (the [slot][4 units] layout made that load 2-way conflicted by
+    //     construction: 17.5 M excess wavefronts per 1 M units, profiles/r2a).
+    static constexpr int HALF_S = (NS + 1) * 2 + (((NS + 1) * 2) % 4 == 2 ? 0 : 2);     // doubles; HALF_S / 2 odd
+    static constexpr int TILE = 2 * HALF_S;                           // doubles per stage tile
+    static constexpr int TILE_S = TILE + ((TILE % 16 == 4 || TILE % 16 == 12) ? 0 : ((4 - TILE % 16) + 16) % 16);   // == 4 or 12 (mod 16)
+    static constexpr int PASS_S = 4 * TILE_S + ((8 - (4 * TILE_S) % 16) + 16) % 16;                                 // == 8 (mod 16)
     // per-warp stride: a multiple of 512 bytes, so that the TMA's 64-byte swizzle (a function of address bits 7..8) is
     // the same for every warp's output boxes
     static constexpr size_t SMEM_PER_WARP = (sizeof(double) * 2 * PASS_S + 511) / 512 * 512;
@@ -375,23 +381,35 @@ template <bool ARM> struct SfCfg {
     static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
     static constexpr size_t SMEM = SMEM_TILES + 2 * sizeof(unsigned) * 13 * 32;   // + gather table, staging table
     // TMA output: the [169][8] and [39][8] boxes of a ROUND (both passes) are staged in pass 0's tiles, all four dead once
-    // pass 0 has consumed them (bytes from the warp's base, 128-byte aligned).  The [169] box runs over the zero row of
-    // pass 0's stage-1 tile, which is restored after the TMA has read the box.
+    // pass 0 has consumed them (bytes from the warp's base, 128-byte aligned).  The [169] box runs over the zero slots of
+    // pass 0's stage-1 tile, which are restored after the TMA has read the box.
     __host__ __device__ static constexpr size_t up128(size_t v) { return (v + 127) / 128 * 128; }
     static constexpr size_t BOX_PHI = 0;
     static constexpr size_t BOX_GAM = (sizeof(double) * 169 * 8 + 127) / 128 * 128;
+    // element (slot s, unit w of the pass) of a stage tile, in doubles from the tile's base
+    __host__ __device__ static constexpr int at(int s, int w) { return (w >> 1) * HALF_S + s * 2 + (w & 1); }
 };
+constexpr bool sf_banks_ok(int half, int tile, int pass) {     // all 8 subset sums of the three strides distinct mod 8 (16-byte groups)
+    const int h = (half / 2) % 8, t = (tile / 2) % 8, q = (pass / 2) % 8;
+    bool seen[8] = {};
+    for (int m = 0; m < 8; ++m) {
+        const int v = ((m & 1 ? h : 0) + (m & 2 ? t : 0) + (m & 4 ? q : 0)) % 8;
+        if (seen[v]) return false;
+        seen[v] = true;
+    }
+    return true;
+}
 static_assert(SfCfg<false>::SMEM_PER_WARP % 128 == 0 && SfCfg<true>::SMEM_PER_WARP % 128 == 0, "TMA staging alignment");
 static_assert(SfCfg<false>::BOX_GAM + 39 * 64 <= sizeof(double) * (SfCfg<false>::PASS_S - 8) &&
               SfCfg<true>::BOX_GAM + 39 * 64 <= sizeof(double) * (SfCfg<true>::PASS_S - 8), "staging boxes fit pass 0's tiles");
-static_assert(SfCfg<false>::PASS_S % 16 == 8 && SfCfg<true>::PASS_S % 16 == 8, "pass stride");
-static_assert(SfCfg<false>::TILE_S % 16 == 4 && SfCfg<true>::TILE_S % 16 == 4, "tile stride");
-static_assert(SfCfg<false>::TILE_S >= SfCfg<false>::TILE + 4 && SfCfg<true>::TILE_S >= SfCfg<true>::TILE + 4, "zero row");
+static_assert(sf_banks_ok(SfCfg<false>::HALF_S, SfCfg<false>::TILE_S, SfCfg<false>::PASS_S) &&
+              sf_banks_ok(SfCfg<true>::HALF_S, SfCfg<true>::TILE_S, SfCfg<true>::PASS_S), "conflict-free tile strides");
+static_assert(SfCfg<false>::HALF_S % 2 == 0 && SfCfg<false>::TILE_S % 2 == 0 && SfCfg<false>::WARPS == 8, "tile geometry (no arm): 8 warps per SM");
 
-struct StageSink {      // the warp's tile: compact slots of this lane's (unit, stage) at [stage][unit / 4][slot][unit % 4]
+struct StageSink {      // the warp's tile: slot s of this lane's (unit, stage) at base[2 s], base = &tile[pass][stage][half][0][unit & 1]
     double* base;
-    __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 4] = v; }
-    __device__ __forceinline__ void ju(int i, int j, double v) const { base[SENS_TAB.ju[i][j] * 4] = v; }
+    __device__ __forceinline__ void jx(int i, int j, double v) const { base[SENS_TAB.jx[i][j] * 2] = v; }
+    __device__ __forceinline__ void ju(int i, int j, double v) const { base[SENS_TAB.ju[i][j] * 2] = v; }
     __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
@@ -409,7 +427,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
     const int c0 = l, c1 = l + 8;                  // tangent columns of this lane in phase B
 
     // zero rows of the stage-1 tiles (targets of the gather's structural zeros); step 2 never writes there
-    if (lane < 8) tile[(lane >> 2) * C::PASS_S + C::TILE + (lane & 3)] = 0.0;
+    if (lane < 8) tile[(lane >> 2) * C::PASS_S + C::at(C::NS, lane & 3)] = 0.0;
     // gather table: byte offsets (within a tile, lane's unit included) of the entries of Jacobian columns c0 (low half)
     // and c1 (high half) of this lane, one word per row; structural zeros point at the zero row.  [13][32 lanes].
     unsigned* const goff = reinterpret_cast<unsigned*>(smem_raw + C::SMEM_TILES) + lane;
@@ -424,7 +442,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 if (ok && c == c0) s0 = sl;
                 if (ok && c == c1) s1 = sl;
             }
-            goff[i * 32] = (unsigned)((s0 * 4 + lu) * 8) | ((unsigned)((s1 * 4 + lu) * 8) << 16);
+            goff[i * 32] = (unsigned)(C::at(s0, lu) * 8) | ((unsigned)(C::at(s1, lu) * 8) << 16);
         }
     }
     // staging table (TMA output): byte offsets, from the warp's base, of row i of this lane's two output columns in the
@@ -533,11 +551,11 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 for (int c = 0; c < 13; ++c) xt[c] = __ldcg(Sw + (s * 16 + c) * 32 + r * 8 + u8);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) u[c] = __ldcg(Sw + (13 + c) * 32 + r * 8 + u8);
-                StageSink sink{tile + (u8 >> 2) * C::PASS_S + s * C::TILE_S + (u8 & 3)};
+                StageSink sink{tile + (u8 >> 2) * C::PASS_S + s * C::TILE_S + C::at(0, u8 & 3)};
                 if (TMA_OUT) {                          // the previous round's output boxes have left the tiles
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-                    if (lane < 4) tile[C::TILE + lane] = 0.0;          // pass 0's zero row lay under the [169][8] box
+                    if (lane < 4) tile[C::at(C::NS, lane)] = 0.0;      // pass 0's zero slots lay under the [169][8] box
                 }
                 model_eval<RIGID, true>(a.K, a.K.A, xt, u, k, sink);
             }
@@ -570,7 +588,7 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 // ---- stages 2..4: S_i = [Jx_i | Ju_i] D_i, one copy of the code (rolled: instruction-cache footprint)
 #pragma unroll 1
                 for (int st = 1; st < 4; ++st) {
-                    const double* __restrict__ T = tile + p * C::PASS_S + st * C::TILE_S + lu;
+                    const double* __restrict__ T = tile + p * C::PASS_S + st * C::TILE_S + C::at(0, lu);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
                     // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
@@ -580,8 +598,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #pragma unroll
                         for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
                             if ((j < 13) ? jx_nz(i, j, ARM) : (!RIGID && ju_nz(i, j - 13))) {
-                                const double jv = T[SENS_TAB.col[i][j] * 4];     // broadcast LDS.64, immediate offset
-                                N0[i] = fma(jv, D[0][j], N0[i]);
+                                const double jv = T[SENS_TAB.col[i][j] * 2];     // broadcast LDS.64, immediate offset
+                                // the control rows of the seed are 0 for this lane's first column (c0 < 8) and e_(c1) for its second
+                                if (j < 13) N0[i] = fma(jv, D[0][j], N0[i]);
                                 N1[i] = fma(jv, D[1][j], N1[i]);
                             }
                         }
@@ -1402,7 +1421,8 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 }
 constexpr long FP64_PEAK_FMAS_PER_ITER = 64;
 
-// Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic, 4 asin_sc(x, sqrt(1-x^2)).
+// Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic, 4 asin_sc(x, sqrt(1-x^2)),
+// 5 / 6: the table forms of 4 / 3 (asin_red, 2^(j/32) table) that the identification-sweep kernels use.
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256) k_math_selftest(const double* __restrict__ x, double* __restrict__ out, long n, int which) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1413,8 +1433,10 @@ __global__ void __launch_bounds__(256) k_math_selftest(const double* __restrict_
         case 0: r = fast_rcp(a); break;
         case 1: r = fast_rsqrt(a); break;
         case 2: r = asin_poly(a); break;
-        case 3: r = fast_logistic(a); break;
-        default: { const double c2 = fma(-a, a, 1.0); r = asin_sc(a, c2 > 0.0 ? c2 * fast_rsqrt(c2) : 0.0); } break;
+        case 3: r = fast_logistic<false>(a); break;
+        case 5: { const double c2 = fma(-a, a, 1.0); r = asin_sc<true>(a, c2 > 0.0 ? c2 * fast_rsqrt(c2) : 0.0); } break;
+        case 6: r = fast_logistic<true>(a); break;
+        default: { const double c2 = fma(-a, a, 1.0); r = asin_sc<false>(a, c2 > 0.0 ? c2 * fast_rsqrt(c2) : 0.0); } break;
     }
     out[i] = r;
 }

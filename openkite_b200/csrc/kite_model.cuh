@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "kite_math.cuh"
 
@@ -178,8 +179,12 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     const double ca = xe * irho, sa = v[2] * irho;            // cos/sin(angle of attack)
     // both angles from their (sin, cos) pairs, branch free for any sideslip and any angle of attack (all four
     // quadrants): two interleaved polynomial chains, no division, no libm, no warp divergence (kite_math.cuh)
-    const double ss = asin_sc(sb, cb);
-    const double aoa = atan2_sc(sa, ca);
+    // Table forms of the special functions where the coefficients come from shared memory (identification sweeps): measured
+    // +3.4 % there (shared controls, nothing else on the load path), neutral to -1.2 % on the config-2 kernel, which stays on
+    // the polynomial forms (profiles/r2e_sweep_tables.log)
+    constexpr bool TAB = std::is_volatile<AC>::value;
+    const double ss = asin_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sb, cb);
+    const double aoa = atan2_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sa, ca);
     const double qS = K.cqS * V2;
 
     // ---- aerodynamic force in the wind frame, rotated to body ---------------------------
@@ -212,7 +217,7 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     const double d = d2 * id;
     const double n[3] = {r[0] * id, r[1] * id, r[2] * id};
     const double e = d - K.Lt;
-    const double H = fast_logistic(4.0 * e);                  // K/(1+exp(-4x)), kitemath.cpp:31-34
+    const double H = fast_logistic<TAB || (KITE_EXP_TABLE != 0)>(4.0 * e);                  // K/(1+exp(-4x)), kitemath.cpp:31-34
     const double nv = fma(n[0], vi[0], fma(n[1], vi[1], n[2] * vi[2]));
     const double tens = fma(K.Ks, e, K.Kd * nv);
     const double tau = tens * H;

@@ -221,7 +221,8 @@ def compose(orc, sym, dev):
     # RK4 + sensitivities: primal step + 4 stage Jacobians + S_i = [Jx_i | Ju_i] D_i for stages 2..4 (stage 1 has the
     # identity seed: a copy, no flops; the survey's 27.8 k counted it as a fourth product) + tableau on the 13 x 16 block
     tableau = 3 * 2 * n * T + 3 * 2 * n * T + 2 * n * T                       # D_i = E + a h S, A += w S, [Phi|Gamma] = E + h/6 A
-    o["RK4_SENS_STEP"] = o["RK4_STEP"] + 4 * jac_only + 3 * 2 * nnz * T + tableau
+    # (S_i = [Jx_i | Ju_i] + a h Jx_i S_(i-1): the control Jacobian enters by addition, 7 adds per stage)
+    o["RK4_SENS_STEP"] = o["RK4_STEP"] + 4 * jac_only + 3 * (2 * NNZ_JX * T + NNZ_JU) + tableau
     o["RK4_SENS_STEP_SURVEY"] = 27800
     # EKF predict (kiteEKF.cpp:75-98): RK4 step + Jx at the pre-step state + A = I + J dt + two DENSE 13^3 products + W
     o["EKF_PREDICT"] = o["RK4_STEP"] + sym["rhs_jac"]["flops"] + 2 * NNZ_JX + 2 * (2 * n ** 3) + n * n
@@ -233,7 +234,8 @@ def compose(orc, sym, dev):
     d["RK4_STEP"] = dev["rk4_step"]["flops"]
     d["RHS_JAC"] = dev["rhs_jac"]["flops"]
     # k_sens_fused: primal pass (RK4 step) + 4 x (f + J) (the Jacobian pass recomputes f's intermediates) + phase B
-    d["RK4_SENS_STEP"] = d["RK4_STEP"] + 4 * d["RHS_JAC"] + 3 * 2 * nnz * T + tableau
+    # (phase B: 104 x 16 FMAs per stage for Jx D, and 7 x 8 for the Ju columns -- one FMA per lane of a unit)
+    d["RK4_SENS_STEP"] = d["RK4_STEP"] + 4 * d["RHS_JAC"] + 3 * (2 * NNZ_JX * T + 2 * NNZ_JU * 8) + tableau
     # k_ekf_predict_tma: RK4 step + (f + J) + two SPARSE products  Q = P + dt (P J^T),  Pn = Q + dt (J Q) + W
     d["EKF_PREDICT"] = d["RK4_STEP"] + d["RHS_JAC"] + 2 * (2 * NNZ_JX * n + 2 * n * n) + n * n
     d["COLLOC_SCENARIO"] = M * (d["RHS_JAC"] + 19 + 2 * (NNZ_JX + 1) + 2 * (NNZ_JU + 1) + 15) + 165 * 6 * 2 + 165 * 2

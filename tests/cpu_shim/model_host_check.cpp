@@ -28,6 +28,20 @@ void shim_eval(const kite_params* prm, int kind, const double* x, const double* 
     else model_eval<false, true>(K, A, xx, uu, ff, s);
     std::memcpy(f, ff, sizeof ff);
 }
+// the same through the table forms of the special functions (volatile coefficients = the identification-sweep kernels)
+void shim_eval_tab(const kite_params* prm, int kind, const double* x, const double* u, const double* p, double* f,
+                   double* Jx, double* Ju) {
+    KiteConsts K = make_consts(*prm, kind);
+    AeroCoef A = K.A;
+    if (p) derive_coef(K, p, A);
+    const volatile AeroCoef& Av = A;
+    double xx[13], uu[3], ff[13];
+    std::memcpy(xx, x, sizeof xx); std::memcpy(uu, u, sizeof uu);
+    std::memset(Jx, 0, 169 * 8); std::memset(Ju, 0, 39 * 8);
+    DenseSink s{Jx, Ju};
+    kite_eval<true>(K, Av, xx, uu, ff, s);
+    std::memcpy(f, ff, sizeof ff);
+}
 void shim_rk4(const kite_params* prm, int kind, const double* x, const double* u, const double* p, double h, long n,
               double* xn) {
     KiteConsts K = make_consts(*prm, kind);

@@ -41,6 +41,18 @@ def prm(yaml_path):
     return params_from_yaml(yaml_path)      # same 39-double order as struct kite_params
 
 
+def test_table_forms_of_special_functions(shim, prm, golden):
+    """asin_red / table exponential (the kernels with per-trajectory coefficients) against the goldens."""
+    for n, c in list(golden["rhs"].items()) + list(golden["rhs_id"].items()):
+        x = np.array(c["x"], float); u = np.array(c["u"], float)
+        f = np.zeros(13); Jx = np.zeros((13, 13)); Ju = np.zeros((13, 3))
+        kind = 1 if "p" in c else 0
+        pp = P(np.array(c["p"], float)) if "p" in c else None
+        shim.shim_eval_tab(P(prm), kind, P(x), P(u), pp, P(f), P(Jx), P(Ju))
+        assert_close(f, c["f"], 1e-12, what=f"f tab[{n}]")
+        assert_close(Jx, c["Jx"], 1e-12, what=f"Jx tab[{n}]")
+
+
 def test_device_model_vs_golden(shim, prm, golden):
     for n, c in golden["rhs"].items():
         f, Jx, Ju = shim_eval(shim, prm, 0, c["x"], c["u"])

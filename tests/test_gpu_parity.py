@@ -703,12 +703,16 @@ def test_lean_math_accuracy(eng):
     assert np.abs(got - np.arcsin(xf.cpu().numpy())).max() < 1e-14
     mid = np.abs(xf.cpu().numpy()) < 0.95
     assert np.abs(got[mid] - np.arcsin(xf.cpu().numpy()[mid])).max() < 1e-15
+    got = eng.math_selftest(xf, 5).cpu().numpy()                   # table form (identification-sweep kernels)
+    assert np.abs(got - np.arcsin(xf.cpu().numpy())).max() < 1e-14
+    assert np.abs(got[mid] - np.arcsin(xf.cpu().numpy()[mid])).max() < 1e-15
     xl = torch.from_numpy(np.concatenate([rng.uniform(-60, 60, 200000), [-800.0, 800.0, 0.0]])).cuda()
-    got = eng.math_selftest(xl, 3).cpu().numpy()
     xr = xl.cpu().numpy()
     ref = np.where(xr >= 0, 1 / (1 + np.exp(-np.abs(xr))), np.exp(-np.abs(xr)) / (1 + np.exp(-np.abs(xr))))
-    assert np.abs(got - ref).max() < 1e-15
-    assert np.abs((got[ref > 1e-280] / ref[ref > 1e-280]) - 1).max() < 2e-15
+    for which in (3, 6):                                           # polynomial / 2^(j/32)-table exponential
+        got = eng.math_selftest(xl, which).cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-15, which
+        assert np.abs((got[ref > 1e-280] / ref[ref > 1e-280]) - 1).max() < 2e-15, which
 
 
 def test_rollout_post_stall_fallback(eng, okb, oracle):
