@@ -120,11 +120,21 @@ struct RolloutArgs {
 #define KITE_ROLLOUT_BLOCK 128
 #endif
 constexpr int ROLLOUT_BLOCK = KITE_ROLLOUT_BLOCK;
+#ifndef KITE_ROLLOUT_SMEM_STATE
+#define KITE_ROLLOUT_SMEM_STATE 0     // 1: base state + tableau accumulator in shared memory, 4 CTAs per SM at 128 registers
+#endif
+#ifndef KITE_ROLLOUT_CTAS
+#define KITE_ROLLOUT_CTAS (KITE_ROLLOUT_SMEM_STATE ? 4 : 3)
+#endif
 #ifdef KITE_ROLLOUT_MAXNREG          // experiments: cap registers directly (occupancy between the launch-bounds steps)
 #define KITE_ROLLOUT_ATTR __maxnreg__(KITE_ROLLOUT_MAXNREG)
 #else
-#define KITE_ROLLOUT_ATTR __launch_bounds__(ROLLOUT_BLOCK, 3)
+#define KITE_ROLLOUT_ATTR __launch_bounds__(ROLLOUT_BLOCK, KITE_ROLLOUT_CTAS)
 #endif
+// dynamic shared memory of a rollout CTA: [per-trajectory coefficients (PERCOEF)][x 13 x BLOCK][acc 13 x BLOCK (SMEM_STATE)]
+constexpr size_t rollout_smem_bytes(bool percoef) {
+    return (percoef ? sizeof(AeroCoef) * ROLLOUT_BLOCK : 0) + (KITE_ROLLOUT_SMEM_STATE ? sizeof(double) * 26 * ROLLOUT_BLOCK : 0);
+}
 
 // Global thread index from the special registers, opaque to the optimiser: the rollout recomputes it after the time loop
 // instead of keeping 2 registers alive (or spilled) across the whole horizon.
@@ -137,7 +147,7 @@ __device__ __forceinline__ long fresh_thread_index() {
 }
 
 template <int UMODE, bool RIGID, class AC>
-__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A);
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A, double* st_sh);
 
 template <int UMODE, bool RIGID, bool PERCOEF>
 __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutArgs a) {
@@ -160,13 +170,20 @@ __global__ void KITE_ROLLOUT_ATTR k_rk4_rollout(const __grid_constant__ RolloutA
             reinterpret_cast<AeroCoef*>(rollout_smem)[threadIdx.x] = At;
         }
     }
-    if constexpr (PERCOEF) rollout_body<UMODE, RIGID>(a, x, u, reinterpret_cast<const volatile AeroCoef*>(rollout_smem)[threadIdx.x]);
-    else rollout_body<UMODE, RIGID>(a, x, u, a.K.A);
+    double* const st_sh = reinterpret_cast<double*>(rollout_smem + (PERCOEF ? sizeof(AeroCoef) * ROLLOUT_BLOCK : 0)) + threadIdx.x;
+    if constexpr (PERCOEF) rollout_body<UMODE, RIGID>(a, x, u, reinterpret_cast<const volatile AeroCoef*>(rollout_smem)[threadIdx.x], st_sh);
+    else rollout_body<UMODE, RIGID>(a, x, u, a.K.A, st_sh);
 }
 
 template <int UMODE, bool RIGID, class AC>
-__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A) {
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[13], double (&u)[3], const AC& A, double* st_sh) {
     const long i = fresh_thread_index();
+#if KITE_ROLLOUT_SMEM_STATE
+    double* const xs = st_sh;                                        // x[c] at xs[c * BLOCK], acc[c] at as[c * BLOCK]
+    double* const as = st_sh + 13 * ROLLOUT_BLOCK;
+#pragma unroll
+    for (int c = 0; c < 13; ++c) xs[c * ROLLOUT_BLOCK] = x[c];
+#endif
 
     // Controls of step k.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 2 are pulled into
     // L2 by a register-free prefetch while step k computes, and the (then short-latency) load itself happens at the top
@@ -213,7 +230,15 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
                 up += 3;
             }
         }
+#if KITE_ROLLOUT_SMEM_STATE
+        rk4_step_sm<RIGID, ROLLOUT_BLOCK>(a.K, A, xs, as, u, a.h, a.h6);
+        if (yp || (a.traj && k + 1 == next_save)) {
+#pragma unroll
+            for (int c = 0; c < 13; ++c) x[c] = xs[c * ROLLOUT_BLOCK];
+        }
+#else
         rk4_step<RIGID>(a.K, A, x, u, a.h, a.h6);
+#endif
         if (yp) {                                   // uniform branch: identification cost fused into the rollout
             double e = 0.0;
 #pragma unroll
@@ -232,6 +257,10 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
         }
     }
     const long io = fresh_thread_index();
+#if KITE_ROLLOUT_SMEM_STATE
+#pragma unroll
+    for (int c = 0; c < 13; ++c) x[c] = xs[c * ROLLOUT_BLOCK];
+#endif
 #pragma unroll
     for (int c = 0; c < 13; ++c) a.xf[(long)c * a.ld + io] = x[c];
     if (a.y) a.cost[io] = cost * (1.0 / (double)a.N);
@@ -593,6 +622,11 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                     for (int i = 0; i < 13; ++i) { N0[i] = 0.0; N1[i] = 0.0; }
                     // column-major traversal: the (up to 13) entries J[i][j] of input row j update 26 independent chains
                     // N[i][.], so consecutive DFMAs never depend on each other; columns 13..15 are the control seed
+                    // Operand order matters: a DFMA with three distinct vector-register operands issues every 3 cycles, with two
+                    // every 2 (profiles/r2j_dfma_operands.log).  The two FMAs of an entry share jv; alternating which column goes
+                    // first makes the first FMA of the NEXT entry share D[.][j] with the one before it, so that every FMA finds
+                    // one operand in the reuse cache: ... (D0, jv1) (D1, jv1) (D1, jv2) (D0, jv2) (D0, jv3) ...
+                    int flip = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
 #pragma unroll
@@ -600,8 +634,16 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                             if ((j < 13) ? jx_nz(i, j, ARM) : (!RIGID && ju_nz(i, j - 13))) {
                                 const double jv = T[SENS_TAB.col[i][j] * 2];     // broadcast LDS.64, immediate offset
                                 // the control rows of the seed are 0 for this lane's first column (c0 < 8) and e_(c1) for its second
-                                if (j < 13) N0[i] = fma(jv, D[0][j], N0[i]);
-                                N1[i] = fma(jv, D[1][j], N1[i]);
+                                if (j >= 13) {
+                                    N1[i] = fma(jv, D[1][j], N1[i]);
+                                } else if (flip) {
+                                    N1[i] = fma(jv, D[1][j], N1[i]);
+                                    N0[i] = fma(jv, D[0][j], N0[i]);
+                                } else {
+                                    N0[i] = fma(jv, D[0][j], N0[i]);
+                                    N1[i] = fma(jv, D[1][j], N1[i]);
+                                }
+                                flip ^= 1;
                             }
                         }
                     }
@@ -719,14 +761,16 @@ __device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, cons
                                               double (&y0)[13], double (&y1)[13]) {
 #pragma unroll
     for (int i = 0; i < 13; ++i) { y0[i] = 0.0; y1[i] = 0.0; }
+    int flip = 0;           // alternate the order inside the pairs: every FMA then shares an operand with its predecessor (see k_sens_fused)
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
 #pragma unroll
         for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
             if (jx_nz(i, j, ARM)) {
                 const double jv = T[SENS_TAB.jx[i][j] * 4];
-                y0[i] = fma(jv, v0[j], y0[i]);
-                y1[i] = fma(jv, v1[j], y1[i]);
+                if (flip) { y1[i] = fma(jv, v1[j], y1[i]); y0[i] = fma(jv, v0[j], y0[i]); }
+                else { y0[i] = fma(jv, v0[j], y0[i]); y1[i] = fma(jv, v1[j], y1[i]); }
+                flip ^= 1;
             }
         }
     }

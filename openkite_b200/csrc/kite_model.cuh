@@ -583,6 +583,43 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, doubl
     for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
 }
 
+// The same step with the base state x and the tableau accumulator in SHARED memory (this thread's column, stride ST doubles;
+// volatile: read at the point of use, never cached in registers): 52 registers less across the RHS, which is what a fourth
+// CTA per SM needs (k_rk4_rollout, KITE_ROLLOUT_SMEM_STATE).
+template <bool RIGID, int ST, class AC>
+__device__ __forceinline__ void rk4_step_sm(const KiteConsts& K, const AC& A, double* xs, double* as,
+                                            const double (&u)[3], double h, double h6) {
+    NoSink ns;
+    double k[13], xt[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) xt[i] = xs[i * ST];
+    const double hh = 0.5 * h;
+    const CtrlTerms uc = ctrl_terms(K, A, u);
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        model_eval_c<RIGID, false>(K, A, xt, uc, k, ns);
+        // the pointers are laundered once per stage: the loads below may be scheduled freely inside the stage but cannot be
+        // hoisted out of the loop into registers (x is loop invariant), which is the whole point of keeping it in shared memory
+        int off = 0;
+#ifdef __CUDA_ARCH__
+        asm volatile("" : "+r"(off));                 // (an opaque zero offset keeps the shared address space of the pointers)
+#endif
+        double* const xp = xs + off; double* const ap = as + off;
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+        const double an = (st == 2) ? h : hh;
+        if (st == 0) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { ap[i * ST] = k[i]; xt[i] = fma(an, k[i], xp[i * ST]); }
+        } else if (st < 3) {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { ap[i * ST] = fma(wgt, k[i], ap[i * ST]); xt[i] = fma(an, k[i], xp[i * ST]); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 13; ++i) xp[i * ST] = fma(h6, k[i] + ap[i * ST], xp[i * ST]);
+        }
+    }
+}
+
 // ---- counter-based synthetic inputs (workload definition; identical to oracle::counter_uniform) ----
 __host__ __device__ inline uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ULL;
