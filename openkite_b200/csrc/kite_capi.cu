@@ -258,7 +258,7 @@ int kite_rk4_rollout(kite_ctx* ctx, long B, long ld, long N, double h, const dou
     if (N >= (1L << 31) || save_every >= (1L << 31)) return fail(ctx, KITE_ERR_ARG, "kite_rk4_rollout: N and save_every must be below 2^31");
     if (B == 0) return KITE_OK;
     CK(cudaSetDevice(ctx->device));
-    RolloutArgs a{ctx->K, B, ld, N, h, h / 6.0, x0_d, u_d, p_d, xf_d, traj_d, save_every > 0 ? save_every : 1, y_d, cost_d, status_d, index0};
+    RolloutArgs a{ctx->K, B, ld, N, h, make_rk_tab(h), x0_d, u_d, p_d, xf_d, traj_d, save_every > 0 ? save_every : 1, y_d, cost_d, status_d, index0};
     if (rigid && !u_d) { a.u = x0_d; u_mode = 0; }   // controls do not enter the rigid-body RHS; dummy readable pointer
     if (u_mode <= 1) launch_rollout_01(a, u_mode, rigid, p_d != nullptr, ctx->stream);
     else launch_rollout_23(a, u_mode, rigid, p_d != nullptr, ctx->stream);
@@ -545,7 +545,7 @@ int kite_ekf_predict_batch(kite_ctx* ctx, long B, long ld, double dt, const doub
     CK(cudaMemcpyAsync(ctx->small.ptr, W_h, sizeof(double) * 169, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->counters.reserve(64)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     CK(cudaMemsetAsync((char*)ctx->counters.ptr + 8, 0, 8, ctx->stream));
-    EkfArgs a{ctx->K, B, ld, dt, dt / 6.0, x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
+    EkfArgs a{ctx->K, B, ld, dt, make_rk_tab(dt), x_d, u_d, P_d, xn_d, Pn_d, (const double*)ctx->small.ptr,
               (unsigned long long*)((char*)ctx->counters.ptr + 8), ctx->status_out};
     if (ctx->ekf_lines.reserve(ekf_predict_scratch_bytes())) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     launch_ekf_predict(a, rigid, ctx->K.has_arm != 0, (double*)ctx->ekf_lines.ptr, ctx->stream);
@@ -610,7 +610,7 @@ int kite_math_selftest(kite_ctx* ctx, long n, const double* x_d, double* out_d, 
     LAUNCH_CHECK("k_math_selftest");
     return KITE_OK;
 }
-int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out) {
+static int fp64_peak_impl(kite_ctx* ctx, int iters, double* tflops_out, bool three_operands) {
     if (!ctx || iters <= 0 || !tflops_out) return fail(ctx, KITE_ERR_ARG, "kite_fp64_peak: bad argument");
     CK(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
@@ -619,9 +619,13 @@ int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out) {
     if (ctx->scratch.reserve(sizeof(double) * (size_t)blocks * threads)) return fail(ctx, KITE_ERR_CUDA, "cudaMalloc failed");
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    launch_fp64_peak((double*)ctx->scratch.ptr, iters / 8 + 1, blocks, threads, ctx->stream);   // warm-up
+    auto go = [&](int n) {
+        if (three_operands) launch_fp64_peak3((double*)ctx->scratch.ptr, n, blocks, threads, ctx->stream);
+        else launch_fp64_peak((double*)ctx->scratch.ptr, n, blocks, threads, ctx->stream);
+    };
+    go(iters / 8 + 1);   // warm-up
     CK(cudaEventRecord(e0, ctx->stream));
-    launch_fp64_peak((double*)ctx->scratch.ptr, iters, blocks, threads, ctx->stream);
+    go(iters);
     CK(cudaEventRecord(e1, ctx->stream));
     ctx->launches += 2;
     CK(cudaEventSynchronize(e1));
@@ -632,5 +636,7 @@ int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out) {
     *tflops_out = flops / (ms * 1e-3) / 1e12;
     return KITE_OK;
 }
+int kite_fp64_peak(kite_ctx* ctx, int iters, double* tflops_out) { return fp64_peak_impl(ctx, iters, tflops_out, false); }
+int kite_fp64_peak_reg3(kite_ctx* ctx, int iters, double* tflops_out) { return fp64_peak_impl(ctx, iters, tflops_out, true); }
 
 }  // extern "C"

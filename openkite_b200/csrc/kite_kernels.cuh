@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(128) k_point_eval(const __grid_constant__ Poin
 struct RolloutArgs {
     KiteConsts K;
     long B, ld, N;
-    double h, h6;            // step size and h / 6 (host-computed)
+    double h;
+    RkTab rk;                // RK4 tableau for h (host-computed)
     const double* x0; const double* u; const double* p;
     double* xf; double* traj; long save_every;
     const double* y; double* cost;
@@ -231,13 +232,13 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
             }
         }
 #if KITE_ROLLOUT_SMEM_STATE
-        rk4_step_sm<RIGID, ROLLOUT_BLOCK>(a.K, A, xs, as, u, a.h, a.h6);
+        rk4_step_sm<RIGID, ROLLOUT_BLOCK>(a.K, A, xs, as, u, a.rk);
         if (yp || (a.traj && k + 1 == next_save)) {
 #pragma unroll
             for (int c = 0; c < 13; ++c) x[c] = xs[c * ROLLOUT_BLOCK];
         }
 #else
-        rk4_step<RIGID>(a.K, A, x, u, a.h, a.h6);
+        rk4_step<RIGID>(a.K, A, x, u, a.rk);
 #endif
         if (yp) {                                   // uniform branch: identification cost fused into the rollout
             double e = 0.0;
@@ -725,7 +726,8 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 struct EkfArgs {
     KiteConsts K;
     long B, ld;
-    double dt, dt6;          // step and dt / 6 (host-computed)
+    double dt;
+    RkTab rk;                // RK4 tableau for dt (host-computed)
     const double* x; const double* u; const double* P;
     double* xn; double* Pn;
     const double* W;         // device [169]
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
                 model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
             }
             const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.rk);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
@@ -999,7 +1001,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
 #pragma unroll
             for (int c = 0; c < 3; ++c) __stcg(Xw + (13 + c) * 32 + lane, u[c]);
             const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.dt, a.dt6);
+            rk4_step<RIGID>(a.K, a.K.A, x, u, a.rk);
             if (unit < a.B) {
 #pragma unroll
                 for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
@@ -1464,6 +1466,26 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[(long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 constexpr long FP64_PEAK_FMAS_PER_ITER = 64;
+// The same with THREE distinct vector-register operands per DFMA (a_i = a_i b_i + c_i, b_i and c_i per-thread values): the FP64
+// pipe then issues one warp instruction every 3 cycles instead of every 2 (operand delivery, not the multiplier, is the limit):
+// the practical ceiling of register-operand code such as the kite RHS (profiles/r2j_dfma_operands.log).
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256) k_fp64_peak3(double* out, int iters, double seed) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = seed + i + threadIdx.x; b[i] = 0.9999999 + 1e-9 * (i + threadIdx.x * seed); c[i] = 1e-7 * (i + 1) * seed + 1e-13 * threadIdx.x; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b[i], c[i]);
+        }
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += a[i];
+    out[(long)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
 
 // Accuracy self-test of kite_math.cuh on the real MUFU seeds: which = 0 rcp, 1 rsqrt, 2 asin_poly, 3 logistic, 4 asin_sc(x, sqrt(1-x^2)),
 // 5 / 6: the table forms of 4 / 3 (asin_red, 2^(j/32) table) that the identification-sweep kernels use.

@@ -19,5 +19,6 @@ void launch_colloc_eval(const CollocArgs& a, bool percoef, int fmt, cudaStream_t
 void launch_colloc_cost(const CostArgs& a, cudaStream_t s);
 void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s);
 void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s);
+void launch_fp64_peak3(double* out, int iters, int blocks, int threads, cudaStream_t s);
 inline unsigned blocks_for(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 }  // namespace kite

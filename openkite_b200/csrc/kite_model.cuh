@@ -207,9 +207,16 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     double M[3][3], nq;
     attitude_matrix(s, a, M, nq);
 
+    // Matrix-vector products are written as COLUMN sweeps: the three FMAs of a sweep share v[j] in the same operand slot, so two of
+    // them find it in the register-reuse cache and issue in 2 cycles instead of 3 (three distinct vector-register operands cost
+    // an extra cycle on the FP64 pipe: profiles/r2j_dfma_operands.log).  Same for M^T n and the quaternion rate below.
     double vi[3];   // inertial velocity = r_dot
 #pragma unroll
-    for (int i = 0; i < 3; ++i) vi[i] = fma(M[i][0], v[0], fma(M[i][1], v[1], M[i][2] * v[2]));
+    for (int i = 0; i < 3; ++i) vi[i] = M[i][2] * v[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vi[i] = fma(M[i][1], v[1], vi[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vi[i] = fma(M[i][0], v[0], vi[i]);
 
     // ---- tether: R = -tau n, tau = (Ks (d-Lt) + Kd n.vi) * logistic(4 (d-Lt)) -------------
     const double d2 = fma(r[0], r[0], fma(r[1], r[1], r[2] * r[2]));
@@ -223,7 +230,11 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     const double tau = tens * H;
     double m[3];    // M^T n
 #pragma unroll
-    for (int i = 0; i < 3; ++i) m[i] = fma(M[0][i], n[0], fma(M[1][i], n[1], M[2][i] * n[2]));
+    for (int i = 0; i < 3; ++i) m[i] = M[2][i] * n[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m[i] = fma(M[1][i], n[1], m[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m[i] = fma(M[0][i], n[0], m[i]);
     const double Rb[3] = {-tau * m[0], -tau * m[1], -tau * m[2]};     // only consumed by the tether-arm moment and the Jacobian
 
     // ---- v_dot = (Faero + T e1 + R_b)/m + g M^T e3 - w x v ---------------------------------
@@ -263,10 +274,11 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     f[6] = vi[0]; f[7] = vi[1]; f[8] = vi[2];
     const double mu = (0.5 * K.lambda) * (nq - 1.0);
     const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};         // q_dot = q (x) [0, w/2] + mu q
-    f[9] = fma(mu, s, -fma(a[0], hw[0], fma(a[1], hw[1], a[2] * hw[2])));
-    f[10] = fma(mu, a[0], fma(s, hw[0], fma(a[1], hw[2], -a[2] * hw[1])));
-    f[11] = fma(mu, a[1], fma(s, hw[1], fma(a[2], hw[0], -a[0] * hw[2])));
-    f[12] = fma(mu, a[2], fma(s, hw[2], fma(a[0], hw[1], -a[1] * hw[0])));
+    // (sweeps over hw[2], hw[1], hw[0], mu: each shares its second operand across the four rows)
+    f[9] = -a[2] * hw[2];                 f[10] = a[1] * hw[2];                 f[11] = -a[0] * hw[2];                f[12] = s * hw[2];
+    f[9] = fma(-a[1], hw[1], f[9]);       f[10] = fma(-a[2], hw[1], f[10]);     f[11] = fma(s, hw[1], f[11]);         f[12] = fma(a[0], hw[1], f[12]);
+    f[9] = fma(-a[0], hw[0], f[9]);       f[10] = fma(s, hw[0], f[10]);         f[11] = fma(a[2], hw[0], f[11]);      f[12] = fma(-a[1], hw[0], f[12]);
+    f[9] = fma(s, mu, f[9]);              f[10] = fma(a[0], mu, f[10]);         f[11] = fma(a[1], mu, f[11]);         f[12] = fma(a[2], mu, f[12]);
 
     if constexpr (JAC) {
         // =========================== gradients w.r.t. v of the aero scalars =======================
@@ -552,18 +564,30 @@ __device__ __forceinline__ void model_eval_c(const KiteConsts& K, const AC& A, c
 #endif
 constexpr int STAGE_UNROLL = KITE_STAGE_UNROLL;     // 1: one copy of the RHS in the instruction stream (rolled stage loop)
 // One classical RK4 step in registers (kitemath.cpp:36-51): x <- x + h/6 (k1 + 2 k2 + 2 k3 + k4).
-// h6 = h / 6 comes from the host (same correctly rounded quotient): an FP64 division in the time loop costs a MUFU seed,
-// a Newton chain and a slow-path CALL per step.
+// Tableau of the classical RK4 step for one step size, filled on the host and read from the kernel's constant bank:
+//   an[st] = offset of the NEXT stage (h/2, h/2, h, -), w[st] = weight (1, 2, 2, 1), h6 = h / 6.
+// Indexed by the (uniform) stage counter they arrive as uniform-register operands: `fma(an, k, x)` then reads two vector
+// registers instead of three (an FP64 instruction with three distinct vector-register operands issues every 3 cycles, not 2:
+// profiles/r2j_dfma_operands.log), and h / 6 is not an FP64 division (MUFU seed + Newton chain + slow-path CALL) per step.
+struct RkTab {
+    double an[4], w[4], h6;
+};
+__host__ __device__ inline RkTab make_rk_tab(double h) {
+    RkTab t;
+    t.an[0] = 0.5 * h; t.an[1] = 0.5 * h; t.an[2] = h; t.an[3] = 0.0;
+    t.w[0] = 1.0; t.w[1] = 2.0; t.w[2] = 2.0; t.w[3] = 1.0;
+    t.h6 = h / 6.0;
+    return t;
+}
 template <bool RIGID, class AC>
 __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, double (&x)[13], const double (&u)[3],
-                                         double h, double h6) {
+                                         const RkTab& rk) {
     // The four stages run as a real loop (one copy of the RHS in the instruction stream: the fully unrolled body
     // was ~100 KB of SASS and stalled on instruction fetch, profiles/r1a_rollout_ncu_summary.txt).
     NoSink ns;
     double k[13], acc[13], xt[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) { acc[i] = 0.0; xt[i] = x[i]; }
-    const double hh = 0.5 * h;
 #if KITE_HOIST_U
     const CtrlTerms uc = ctrl_terms(K, A, u);                    // the control is held for all four stages
 #endif
@@ -574,13 +598,13 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, doubl
 #else
         model_eval<RIGID, false>(K, A, xt, u, k, ns);
 #endif
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;     // tableau weights b = (1,2,2,1)/6
-        const double an = (st == 2) ? h : hh;                    // next stage offset a = (1/2, 1/2, 1)
+        const double wgt = rk.w[st];                             // tableau weights b = (1,2,2,1)/6
+        const double an = rk.an[st];                             // next stage offset a = (1/2, 1/2, 1)
 #pragma unroll
         for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], x[i]); }
     }
 #pragma unroll
-    for (int i = 0; i < 13; ++i) x[i] = fma(h6, acc[i], x[i]);
+    for (int i = 0; i < 13; ++i) x[i] = fma(rk.h6, acc[i], x[i]);
 }
 
 // The same step with the base state x and the tableau accumulator in SHARED memory (this thread's column, stride ST doubles;
@@ -588,12 +612,11 @@ __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, doubl
 // CTA per SM needs (k_rk4_rollout, KITE_ROLLOUT_SMEM_STATE).
 template <bool RIGID, int ST, class AC>
 __device__ __forceinline__ void rk4_step_sm(const KiteConsts& K, const AC& A, double* xs, double* as,
-                                            const double (&u)[3], double h, double h6) {
+                                            const double (&u)[3], const RkTab& rk) {
     NoSink ns;
     double k[13], xt[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) xt[i] = xs[i * ST];
-    const double hh = 0.5 * h;
     const CtrlTerms uc = ctrl_terms(K, A, u);
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
@@ -605,8 +628,8 @@ __device__ __forceinline__ void rk4_step_sm(const KiteConsts& K, const AC& A, do
         asm volatile("" : "+r"(off));                 // (an opaque zero offset keeps the shared address space of the pointers)
 #endif
         double* const xp = xs + off; double* const ap = as + off;
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-        const double an = (st == 2) ? h : hh;
+        const double wgt = rk.w[st];
+        const double an = rk.an[st];
         if (st == 0) {
 #pragma unroll
             for (int i = 0; i < 13; ++i) { ap[i * ST] = k[i]; xt[i] = fma(an, k[i], xp[i * ST]); }
@@ -615,7 +638,7 @@ __device__ __forceinline__ void rk4_step_sm(const KiteConsts& K, const AC& A, do
             for (int i = 0; i < 13; ++i) { ap[i * ST] = fma(wgt, k[i], ap[i * ST]); xt[i] = fma(an, k[i], xp[i * ST]); }
         } else {
 #pragma unroll
-            for (int i = 0; i < 13; ++i) xp[i * ST] = fma(h6, k[i] + ap[i * ST], xp[i * ST]);
+            for (int i = 0; i < 13; ++i) xp[i * ST] = fma(rk.h6, k[i] + ap[i * ST], xp[i * ST]);
         }
     }
 }

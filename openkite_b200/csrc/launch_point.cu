@@ -27,4 +27,7 @@ void launch_math_selftest(const double* x, double* out, long n, int which, cudaS
 void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s) {
     k_fp64_peak<0><<<blocks, threads, 0, s>>>(out, iters, 1.0);
 }
+void launch_fp64_peak3(double* out, int iters, int blocks, int threads, cudaStream_t s) {
+    k_fp64_peak3<0><<<blocks, threads, 0, s>>>(out, iters, 1.0);
+}
 }  // namespace kite

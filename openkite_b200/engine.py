@@ -118,6 +118,7 @@ def load_library():
     L.kite_allgather.argtypes = [vp, dp, dp, lg]
     L.kite_comm_destroy.argtypes = [vp]
     L.kite_fp64_peak.argtypes = [vp, ip, C.POINTER(db)]
+    L.kite_fp64_peak_reg3.argtypes = [vp, ip, C.POINTER(db)]
     L.kite_math_selftest.argtypes = [vp, lg, dp, dp, ip]
     _lib = L
     return L
@@ -380,8 +381,9 @@ class Engine:
         self._ck(self.L.kite_math_selftest(self.ctx, x.numel(), _ptr(x), _ptr(out), which))
         return out
 
-    def fp64_peak(self, iters=20000):
+    def fp64_peak(self, iters=20000, three_register_operands=False):
         self._use_torch_stream()
         out = C.c_double()
-        self._ck(self.L.kite_fp64_peak(self.ctx, iters, C.byref(out)))
+        fn = self.L.kite_fp64_peak_reg3 if three_register_operands else self.L.kite_fp64_peak
+        self._ck(fn(self.ctx, iters, C.byref(out)))
         return out.value

@@ -122,7 +122,7 @@ int main() {
     K.has_arm = 1;
     { NullSink s; kite_eval<true>(K, K.A, x, u, f, s); report("rhs_jac_arm", s.nx, s.nu); }
     K.has_arm = 0;
-    { real_t xx[13]; for (int i = 0; i < 13; ++i) xx[i] = x[i]; rk4_step<false>(K, K.A, xx, u, real_t(1e-3), real_t(1e-3 / 6.0)); report("rk4_step"); }
+    { real_t xx[13]; for (int i = 0; i < 13; ++i) xx[i] = x[i]; RkTab rk = make_rk_tab(real_t(1e-3)); tally() = Tally(); rk4_step<false>(K, K.A, xx, u, rk); report("rk4_step"); }
     { NoSink s; rigid_eval<false>(K, x, f, s); report("rigid_rhs"); }
     { NullSink s; rigid_eval<true>(K, x, f, s); report("rigid_rhs_jac", s.nx, s.nu); }
     return 0;

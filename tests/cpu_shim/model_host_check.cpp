@@ -49,7 +49,7 @@ void shim_rk4(const kite_params* prm, int kind, const double* x, const double* u
     if (p) derive_coef(K, p, A);
     double xx[13], uu[3];
     std::memcpy(xx, x, sizeof xx); std::memcpy(uu, u, sizeof uu);
-    for (long k = 0; k < n; ++k) { if (kind == 2) rk4_step<true>(K, A, xx, uu, h, h / 6.0); else rk4_step<false>(K, A, xx, uu, h, h / 6.0); }
+    for (long k = 0; k < n; ++k) { if (kind == 2) rk4_step<true>(K, A, xx, uu, make_rk_tab(h)); else rk4_step<false>(K, A, xx, uu, make_rk_tab(h)); }
     std::memcpy(xn, xx, sizeof xx);
 }
 }
