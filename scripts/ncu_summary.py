@@ -54,7 +54,7 @@ def main():
         rows = raw_rows(rep)
         kname = key.split("@")[0].split("<")[0]
         row = [r for r in rows if kname in r["Kernel Name"][1]][-1]
-        short = re.sub(r"[^a-z0-9_]", "", kname)
+        short = re.sub(r"[^A-Za-z0-9]+", "_", key).strip("_")       # kernel + template arguments + size: one file per key
         out = os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.txt" % (tag, short))
         lines = ["ncu --set full --clock-control none --import-source on; key %s; report %s" % (key, os.path.basename(rep)), "-----",
                  "Kernel Name = %s" % row["Kernel Name"][1], "Block Size = %s" % row["Block Size"][1], "Grid Size = %s" % row["Grid Size"][1]]
