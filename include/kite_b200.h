@@ -192,7 +192,8 @@ int kite_rk4_sens_rollout(kite_ctx* ctx, long B, long ld, long N, double h, cons
  *   G_d  [M*15][ld]           G = (compD (x) I15) X - tau F
  *   JX_d [M*225][ld] or NULL  node blocks d f_s/d x_s (15x15 row-major per node); AugJacobian's varying part is -tau*JX
  *   JU_d [M*60][ld]  or NULL  node blocks d f_s/d u_s (15x4)
- *   gnorm_d [ld] or NULL      per-scenario ||G||_2^2 (warp-shuffle reduction over the nodes) */
+ *   gnorm_d [ld] or NULL      per-scenario ||G||_2^2 (warp-shuffle reduction over the nodes)
+ * With JX_d = JU_d = NULL a values-only kernel runs (no Jacobian code: what a line search asks for). */
 int kite_colloc_eval(kite_ctx* ctx, long B, long ld, int M, const double* compD_h, double tau, const double* sx_h,
                      const double* su_h, const double* z_d, const double* p_d, double* G_d, double* JX_d, double* JU_d,
                      double* gnorm_d);

@@ -462,8 +462,23 @@ static int colloc_eval_impl(kite_ctx* ctx, long B, long ld, int M, const double*
     for (int i = 0; i < 15; ++i) { a.sx[i] = sx_h[i]; a.isx[i] = 1.0 / sx_h[i]; }
     for (int i = 0; i < 4; ++i) { a.su[i] = su_h[i]; a.isu[i] = 1.0 / su_h[i]; }
     a.compD = (const double*)ctx->small.ptr;
+    a.cd_compact = 0;
+    if (M <= 16) {                       // compact rows for the constant bank (summation order = ascending column, as the dense walk)
+        bool fits = true;
+        for (int k = 0; k < M && fits; ++k) {
+            int n = 0;
+            for (int l = 0; l < M; ++l)
+                if (compD_h[(size_t)k * M + l] != 0.0) {
+                    if (n == 8) { fits = false; break; }
+                    a.cd_col[k][n] = (signed char)l; a.cd_val[k][n] = compD_h[(size_t)k * M + l]; ++n;
+                }
+            a.cd_nz[k] = n;
+        }
+        a.cd_compact = fits ? 1 : 0;
+    }
     a.z = z_d; a.p = p_d; a.G = G_d; a.JX = JX_d; a.JU = JU_d; a.gnorm = gnorm_d; a.status = ctx->status_out;
-    launch_colloc_eval(a, p_d != nullptr, sparse ? (ctx->K.has_arm ? 2 : 1) : 0, ctx->stream);
+    const int fmt = sparse ? (ctx->K.has_arm ? 2 : 1) : ((JX_d || JU_d) ? 0 : 3);      // no Jacobian output: no Jacobian code
+    launch_colloc_eval(a, p_d != nullptr, fmt, ctx->stream);
     LAUNCH_CHECK("k_colloc_eval");
     return KITE_OK;
 }

@@ -1204,6 +1204,12 @@ struct CollocArgs {
     double tau;
     double sx[15], isx[15], su[4], isu[4];
     const double* compD;     // device [M][M]
+    // compact rows of compD in the constant bank (M <= 16 nodes, <= 8 non-zeros per row: every NMPC / test configuration of the
+    // reference): column indices and values of row k, read with the warp-uniform k -- no dependent global load per column
+    int cd_compact;          // 1: use cd_nz / cd_col / cd_val, 0: walk the dense row in global memory
+    int cd_nz[16];
+    signed char cd_col[16][8];
+    double cd_val[16][8];
     const double* z; const double* p;
     double* G; double* JX; double* JU; double* gnorm;
     int32_t* status;         // [ld] per-scenario flags, OR over the nodes, or null
@@ -1259,7 +1265,7 @@ struct CollocSparseSink {       // value of entry (i, j) of the node block goes 
     __device__ __forceinline__ void aero(double, double, double) const {}
 };
 
-// FMT 0: dense 15 x 15 / 15 x 4 node blocks (JX, JU);  1 / 2: structural non-zeros only (JV), without / with tether arm.
+// FMT 0: dense 15 x 15 / 15 x 4 node blocks (JX, JU);  1 / 2: structural non-zeros only (JV), without / with tether arm;  3: G only.
 template <bool PERCOEF, int NPB, int FMT>
 __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant__ CollocArgs a) {
     __shared__ double red[NPB][32];                // partial ||G||^2 per node row of the block
@@ -1291,7 +1297,11 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             for (int c = 0; c < 3; ++c) u[c] = a.isu[c] * __ldg(zu + (long)c * a.ld);
             const double u3 = a.isu[3] * __ldg(zu + 3L * a.ld);
             flags |= singularity_flags<false>(x);
-            if constexpr (FMT == 0) {
+            if constexpr (FMT == 3) {              // constraint values only (what a line search asks for): no Jacobian code at all
+                NoSink sink;
+                if constexpr (PERCOEF) kite_eval<false>(a.K, Av, x, u, f, sink);
+                else kite_eval<false>(a.K, a.K.A, x, u, f, sink);
+            } else if constexpr (FMT == 0) {
                 CollocSink sink{a.JX ? a.JX + (long)(k * 225) * a.ld + s : nullptr,
                                 a.JU ? a.JU + (long)(k * 60) * a.ld + s : nullptr, a.ld, a.sx, a.isx, a.isu};
                 if constexpr (PERCOEF) kite_eval<true>(a.K, Av, x, u, f, sink);
@@ -1338,12 +1348,22 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             double acc[15];
 #pragma unroll
             for (int c = 0; c < 15; ++c) acc[c] = 0.0;
-            for (int l = 0; l < M; ++l) {
-                const double dkl = __ldg(a.compD + k * M + l);
-                if (dkl != 0.0) {                  // warp-uniform: k is the same for the whole warp
-                    const double* zl = a.z + (long)(l * 15) * a.ld + s;
+            if (a.cd_compact) {                    // (uniform) the row's non-zeros come from the constant bank: the 15 loads of
+                const int nz = a.cd_nz[k];         // every column are independent of everything but the column index
+                for (int t = 0; t < nz; ++t) {
+                    const double dkl = a.cd_val[k][t];
+                    const double* zl = a.z + (long)(a.cd_col[k][t] * 15) * a.ld + s;
 #pragma unroll
                     for (int c = 0; c < 15; ++c) acc[c] = fma(dkl, __ldg(zl + (long)c * a.ld), acc[c]);
+                }
+            } else {
+                for (int l = 0; l < M; ++l) {
+                    const double dkl = __ldg(a.compD + k * M + l);
+                    if (dkl != 0.0) {              // warp-uniform: k is the same for the whole warp
+                        const double* zl = a.z + (long)(l * 15) * a.ld + s;
+#pragma unroll
+                        for (int c = 0; c < 15; ++c) acc[c] = fma(dkl, __ldg(zl + (long)c * a.ld), acc[c]);
+                    }
                 }
             }
 #pragma unroll

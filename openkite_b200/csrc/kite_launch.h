@@ -15,7 +15,7 @@ long sens_fused_max_warps();   // upper bound of the resident warps of the persi
 void launch_ekf_predict(const EkfArgs& a, bool rigid, bool arm, double* lines, cudaStream_t s);
 size_t ekf_predict_scratch_bytes();   // pre-step state lines of the resident warps of the TMA kernel (independent of B)
 void launch_ekf_update(const EkfUpdArgs& a, cudaStream_t s);
-void launch_colloc_eval(const CollocArgs& a, bool percoef, int fmt, cudaStream_t s);   // fmt 0 dense, 1 / 2 compact (no arm / arm)
+void launch_colloc_eval(const CollocArgs& a, bool percoef, int fmt, cudaStream_t s);   // fmt 0 dense, 1 / 2 compact (no arm / arm), 3 values only
 void launch_colloc_cost(const CostArgs& a, cudaStream_t s);
 void launch_math_selftest(const double* x, double* out, long n, int which, cudaStream_t s);
 void launch_fp64_peak(double* out, int iters, int blocks, int threads, cudaStream_t s);

@@ -8,11 +8,13 @@ void launch_colloc_eval(const CollocArgs& a, bool percoef, int fmt, cudaStream_t
     dim3 block(32, KITE_COLLOC_NPB);
     constexpr int N = KITE_COLLOC_NPB;
     if (percoef) {
-        if (fmt == 0) k_colloc_eval<true, N, 0><<<gb, block, 0, s>>>(a);
+        if (fmt == 3) k_colloc_eval<true, N, 3><<<gb, block, 0, s>>>(a);
+        else if (fmt == 0) k_colloc_eval<true, N, 0><<<gb, block, 0, s>>>(a);
         else if (fmt == 1) k_colloc_eval<true, N, 1><<<gb, block, 0, s>>>(a);
         else k_colloc_eval<true, N, 2><<<gb, block, 0, s>>>(a);
     } else {
-        if (fmt == 0) k_colloc_eval<false, N, 0><<<gb, block, 0, s>>>(a);
+        if (fmt == 3) k_colloc_eval<false, N, 3><<<gb, block, 0, s>>>(a);
+        else if (fmt == 0) k_colloc_eval<false, N, 0><<<gb, block, 0, s>>>(a);
         else if (fmt == 1) k_colloc_eval<false, N, 1><<<gb, block, 0, s>>>(a);
         else k_colloc_eval<false, N, 2><<<gb, block, 0, s>>>(a);
     }

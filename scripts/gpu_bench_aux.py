@@ -56,6 +56,9 @@ if "colloc" in which:
     out = (eng.empty(M * 15, B), eng.empty(M * 225, B), eng.empty(M * 60, B), eng.empty(B))
     ms = timeit(lambda: eng.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], out=out))
     report("colloc_eval G+JX+JU", B, ms, 31600.0, 8.0 * (209 + 165 + 11 * 285))
+    outs = (out[0], eng.empty(M * eng.colloc_nnz_per_node(), B), out[3])
+    ms = timeit(lambda: eng.colloc_eval_sparse(z, M, compD, 0.25, c["sx"], c["su"], out=outs))
+    report("colloc_eval_sparse G+JV", B, ms, 31600.0, 8.0 * (209 + 165 + 11 * eng.colloc_nnz_per_node()))
     out2 = (out[0], None, None, out[3])
     ms = timeit(lambda: eng.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], out=out2))
     report("colloc_eval G only", B, ms, 11 * 420.0 + 2000, 8.0 * (209 + 165))

@@ -566,6 +566,9 @@ def test_colloc_sparse_blocks_match_dense(okb, params, oracle, golden):
             G, JX, JU, gn = e.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], p=p)
             G2, JV, gn2 = e.colloc_eval_sparse(z, M, compD, 0.25, c["sx"], c["su"], p=p)
             assert torch.equal(G, G2) and torch.equal(gn, gn2)
+            G3, none_x, none_u, gn3 = e.colloc_eval(z, M, compD, 0.25, c["sx"], c["su"], p=p, want_jac=False)   # values-only kernel
+            assert none_x is None and none_u is None
+            assert_close(aos(G3), aos(G), 1e-13, what="G of the values-only kernel"); assert_close(gn3.cpu().numpy(), gn.cpu().numpy(), 1e-12, what="gnorm")
             dense = torch.cat([JX.reshape(M, 15, 15, B), JU.reshape(M, 15, 4, B)], dim=2)       # [M, 15, 19, B]
             picked = dense[:, rows, cols, :]                                                    # [M, nnz, B]
             assert torch.equal(picked.reshape(M * nnz, B), JV)
