@@ -758,7 +758,7 @@ struct SmemSink {       // compact slots of this lane's filter in the warp's sha
 };
 
 // y[i] += sum_j J[i][j] v[j] for two vectors at once, J from the shared tile column of this lane's filter
-template <bool ARM, bool RIGID>
+template <bool ARM, bool RIGID, int STRIDE = 4>      // STRIDE: filters per tile row ([slot][STRIDE])
 __device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, const double (&v0)[13], const double (&v1)[13],
                                               double (&y0)[13], double (&y1)[13]) {
 #pragma unroll
@@ -769,7 +769,7 @@ __device__ __forceinline__ void ekf_jx_times2(const double* __restrict__ T, cons
 #pragma unroll
         for (int i = (RIGID ? 6 : 0); i < 13; ++i) {
             if (jx_nz(i, j, ARM)) {
-                const double jv = T[SENS_TAB.jx[i][j] * 4];
+                const double jv = T[SENS_TAB.jx[i][j] * STRIDE];
                 if (flip) { y1[i] = fma(jv, v1[j], y1[i]); y0[i] = fma(jv, v0[j], y0[i]); }
                 else { y0[i] = fma(jv, v0[j], y0[i]); y1[i] = fma(jv, v1[j], y1[i]); }
                 flip ^= 1;
@@ -873,17 +873,20 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
 
 // ================================================================================================
 // EKF predict, round-based with TMA boxes (the product path when the covariance layout is TMA-addressable: 16-byte
-// aligned base and pitch, even B).  Same arithmetic as k_ekf_predict; what changes is how P moves and how much of the
-// Jacobian is in flight.  A warp owns groups of 32 filters:
-//   step 1 (lane = filter): RK4 step -> xn; the pre-step state and the control are parked in the warp's L2-resident line.
+// aligned base and pitch, even B).  Same arithmetic as k_ekf_predict; what changes is how P moves and where the Jacobian
+// waits.  A warp owns groups of 32 filters:
+//   step 1 (lane = filter, 32 filters): ONE evaluation of f and d f/d x at the pre-step state gives the Jacobian AND the first
+//       RK4 stage k1 (the reference evaluates both at the same point, kiteEKF.cpp:80,93); three more RHS evaluations finish the
+//       step -> xn.  The 99 Jacobian entries of a filter go to the warp's line of an L2-resident scratch laid out
+//       [round][slot][8 filters]; the filters of round 0 also write them straight into the shared tile.  (Round 1 evaluated
+//       the Jacobian once per round with 4 replica lanes per filter: 30 % of the kernel's time for 3 redundant evaluations,
+//       profiles/r2a ncu source page; a 32-filter tile in shared memory would leave room for 4 warps per SM.)
 //   four rounds of 8 filters:
-//     Jacobian at the pre-step state with lane = (filter, replica): the four replicas of a filter compute the same
-//       entries and replica 0 writes them (the evaluation costs the same issue slots for 8 or 32 active lanes; what it
-//       buys is a 6 KB tile [pass][slot][4 filters] instead of 26 KB, i.e. room for the covariance boxes);
-//     the [169][8 filters] box of P (64-byte rows, 64-byte swizzle) arrives by ONE TMA tensor load issued half a round
-//       ahead; phase B (8 lanes = filter, 2 passes of 4 filters) reads the rows of P from the box, writes Q = P A^T back
-//       IN PLACE (a lane only overwrites what it read), reads the columns of Q from the same box (the box is the
-//       transpose buffer), writes the columns of Pn = A Q + W in place, and the box leaves by ONE TMA tensor store.
+//     the round's [99][8] Jacobian tile arrives by ONE 1-D bulk copy (cp.async.bulk, mbarrier) issued a round ahead into the
+//       other of two tile buffers; the [169][8 filters] box of P (64-byte rows, 64-byte swizzle) arrives by ONE TMA tensor
+//       load issued half a round ahead; phase B (8 lanes = filter, 2 passes of 4 filters) reads the rows of P from the box,
+//       writes Q = P A^T back IN PLACE (a lane only overwrites what it read), reads the columns of Q from the same box (the
+//       box is the transpose buffer), writes the columns of Pn = A Q + W in place, and the box leaves by ONE TMA tensor store.
 //   The LSU sees conflict-free shared accesses through per-lane offset tables instead of 52 eight-sector global accesses
 //   with 64-bit address arithmetic per pass (profiles/r1zb_ekf_before_ncu_summary.txt: LSU data pipe 63 % busy).
 // ================================================================================================
@@ -891,29 +894,34 @@ struct EkfTmaArgs {
     alignas(64) CUtensorMap tmP;      // [1][169][B] rows of ld doubles, box [1][169][8 filters], 64-byte swizzle
     alignas(64) CUtensorMap tmPn;
     EkfArgs e;
-    double* Xw;                       // scratch: [resident warp][x(13) | u(3)][32 filters]
+    double* Jw;                       // scratch: [resident warp][4 rounds][NS slots][8 filters]
 };
-constexpr long ET_SCRATCH_PER_WARP = 16L * 32;
 template <bool ARM> struct EtCfg {
     static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM - 7;          // state-Jacobian slots (no Ju)
-    static constexpr int TILE_S = NS * 4;                                         // doubles per pass tile [slot][4 filters]
+    static constexpr int TILE_D = NS * 8;                                         // doubles per round tile [slot][8 filters]
+    static constexpr unsigned TILE_BYTES = TILE_D * 8;
     static constexpr size_t BOX = (169 * 64 + 511) / 512 * 512;                   // 10816 -> 11264: both boxes see the same swizzle
     static constexpr unsigned BOX_BYTES = 169 * 64;
-    static constexpr size_t PER_WARP = (2 * BOX + sizeof(double) * 2 * TILE_S + 511) / 512 * 512;
+    static constexpr size_t PER_WARP = (2 * BOX + 2 * TILE_BYTES + 511) / 512 * 512;
     static constexpr int FIT = (int)((SF_SMEM_MAX - 8192) / PER_WARP);
     static constexpr int WARPS = FIT < 8 ? FIT : 8;
     static constexpr size_t SMEM_WARPS = PER_WARP * WARPS;
     static constexpr size_t OFF_W = SMEM_WARPS;                                   // W (13 x 13), one copy per CTA
-    static constexpr size_t OFF_TAB = OFF_W + sizeof(double) * 176;               // row / column offset tables [2][13][32] words
-    static constexpr size_t OFF_BAR = OFF_TAB + sizeof(unsigned) * 2 * 13 * 32;   // two mbarriers per warp
-    static constexpr size_t SMEM = OFF_BAR + sizeof(unsigned long long) * 2 * WARPS;
+    static constexpr size_t OFF_BAR = OFF_W + sizeof(double) * 176;               // four mbarriers per warp (2 boxes, 2 tiles)
+    static constexpr size_t SMEM = OFF_BAR + sizeof(unsigned long long) * 4 * WARPS;
+    static constexpr long SCRATCH_PER_WARP = 4L * TILE_D;                         // doubles of L2 scratch per resident warp
 };
 static_assert(EtCfg<false>::SMEM <= SF_SMEM_MAX && EtCfg<true>::SMEM <= SF_SMEM_MAX, "shared memory");
+static_assert(EtCfg<false>::TILE_BYTES % 16 == 0 && EtCfg<true>::TILE_BYTES % 16 == 0, "bulk-copy granularity");
+constexpr long ET_SCRATCH_PER_WARP_MAX = EtCfg<true>::SCRATCH_PER_WARP > EtCfg<false>::SCRATCH_PER_WARP ? EtCfg<true>::SCRATCH_PER_WARP : EtCfg<false>::SCRATCH_PER_WARP;
 
-struct Rep0Sink {       // compact state-Jacobian slots of this lane's filter; only replica 0 of a filter stores
-    double* base;       // &tile[filter / 4][0][filter % 4]
-    bool on;
-    __device__ __forceinline__ void jx(int i, int j, double v) const { if (on) base[SENS_TAB.jx[i][j] * 4] = v; }
+struct EkfTileSink {    // state-Jacobian slot s of this lane's filter: scratch line [round][s][8] (+ the shared tile for round 0)
+    double* g;          // &Jw[lane / 8][0][lane % 8]
+    double* sh;         // &tile0[0][lane] for lanes 0..7, null otherwise
+    __device__ __forceinline__ void jx(int i, int j, double v) const {
+        __stcg(g + SENS_TAB.jx[i][j] * 8, v);
+        if (sh) sh[SENS_TAB.jx[i][j] * 8] = v;
+    }
     __device__ __forceinline__ void ju(int, int, double) const {}
     __device__ __forceinline__ void aero(double, double, double) const {}
 };
@@ -934,34 +942,18 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
     const EkfArgs& a = ta.e;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* const wb = smem_raw + (size_t)warp * C::PER_WARP;              // [box 0][box 1][Jacobian tile]
+    unsigned char* const wb = smem_raw + (size_t)warp * C::PER_WARP;              // [box 0][box 1][tile 0][tile 1]
     double* const Jt = reinterpret_cast<double*>(wb + 2 * C::BOX);
     double* const Ws = reinterpret_cast<double*>(smem_raw + C::OFF_W);
-    unsigned* const rtab = reinterpret_cast<unsigned*>(smem_raw + C::OFF_TAB) + lane;        // rows (r0 | r1 << 16) of entry k
-    unsigned* const ctab = rtab + 13 * 32;                                                   // columns
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::OFF_BAR) + warp * 2;
-    double* const Xw = ta.Xw + ((long)blockIdx.x * C::WARPS + warp) * ET_SCRATCH_PER_WARP;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw + C::OFF_BAR) + warp * 4;   // [box 0, box 1, tile 0, tile 1]
+    double* const Jw = ta.Jw + ((long)blockIdx.x * C::WARPS + warp) * C::SCRATCH_PER_WARP;
     const long ngroups = (a.B + 31) / 32;
     const int lu = lane >> 3, l = lane & 7;
     const int r0 = l, r1 = l + 8;                  // rows of P (first product) = columns of Pn (second product)
     const bool v1 = r1 < 13;
 
     for (int t = threadIdx.x; t < 169; t += blockDim.x) Ws[t] = __ldg(a.W + t);
-    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + lane)) : "memory");
-    if (warp == 0) {
-        // byte offsets inside a box of entry (row, col) for this lane's filter of pass 0 (pass 1: ^ 32), with the TMA's
-        // 64-byte swizzle applied: 16-byte chunk index ^= address bits 7..8 (the same for every box: 512-byte strides)
-        const unsigned base_abs = smem_u32(smem_raw);
-        auto phys = [&](int row, int col) -> unsigned {
-            const unsigned lg = (unsigned)(row * 13 + col) * 64u + (unsigned)lu * 8u;
-            return lg ^ ((((base_abs + lg) >> 7) & 3u) << 4);
-        };
-#pragma unroll
-        for (int k = 0; k < 13; ++k) {
-            rtab[k * 32] = phys(r0, k) | (phys(v1 ? r1 : r0, k) << 16);
-            ctab[k * 32] = phys(k, r0) | (phys(k, v1 ? r1 : r0) << 16);
-        }
-    }
+    if (lane < 4) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + lane)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -975,85 +967,99 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                             "r"((int)first), "r"(0), "r"(0), "r"(bar) : "memory");
         }
     };
+    // Jacobian tile of round r of the current group: scratch line [r] -> tile buffer t & 1, one 1-D bulk copy issued by lane 0
+    auto issue_tile = [&](unsigned t, int r) {
+        if (lane == 0) {
+            const unsigned bar = smem_u32(bars + 2 + (t & 1));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::TILE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(Jt + (t & 1) * C::TILE_D)), "l"(Jw + (long)r * C::TILE_D), "r"(C::TILE_BYTES), "r"(bar) : "memory");
+        }
+    };
     auto claim_group = [&]() -> long {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.next_group, 1ULL);
         return (long)__shfl_sync(0xffffffffu, g, 0);
     };
     unsigned t = 0;                                 // rounds done by this warp (buffer and mbarrier phase bookkeeping)
+    unsigned tile_ph0 = 0, tile_ph1 = 0;            // phases of the two tile barriers (only bulk-copied rounds flip them)
     long g = claim_group();
     if (g < ngroups) issue_load(0, g * 32);
     while (g < ngroups) {
         const long g_next = claim_group();
-        // ---------------- step 1: lane = filter, RK4 step ---------------------------------------------------
+        // ---------------- step 1: lane = filter: Jacobian + k1 at the pre-step state, then the rest of the RK4 step ------
         {
             const long unit = g * 32 + lane;
             const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
-            double x[13], u[3];
+            double x[13], u[3], k[13], acc[13], xt[13];
 #pragma unroll
             for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
 #pragma unroll
             for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
-            // (all loads before the first store: the compiler must assume the scratch aliases the inputs and would
-            // otherwise serialise load - store - load - store, one memory round trip each)
-#pragma unroll
-            for (int c = 0; c < 13; ++c) __stcg(Xw + c * 32 + lane, x[c]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) __stcg(Xw + (13 + c) * 32 + lane, u[c]);
             const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.rk);
+            {
+                // (t is even here: a group has four rounds, so round 0 always uses tile buffer 0)
+                EkfTileSink sink{Jw + (lane >> 3) * C::TILE_D + (lane & 7), lane < 8 ? Jt + lane : nullptr};
+                model_eval<RIGID, true>(a.K, a.K.A, x, u, k, sink);
+            }
+            // the scratch lines of rounds 1..3 are read by the async proxy (bulk copies issued by lane 0)
+            // (each lane orders its own generic-proxy stores before later async-proxy reads; __syncwarp below makes them
+            // visible to lane 0, which issues the copy.  A full __threadfence here cost 5 % of the kernel: ERRBAR + CCTL.IVALL)
+            asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 13; ++c) { acc[c] = k[c]; xt[c] = fma(a.rk.an[0], k[c], x[c]); }
+            __syncwarp();
+            issue_tile(t + 1, 1);                  // buffer 1: last read by the previous group's round 3
+            NoSink ns;
+#pragma unroll 1
+            for (int st = 1; st < 4; ++st) {
+                model_eval<RIGID, false>(a.K, a.K.A, xt, u, k, ns);
+                const double wgt = a.rk.w[st], an = a.rk.an[st];
+#pragma unroll
+                for (int c = 0; c < 13; ++c) { acc[c] = fma(wgt, k[c], acc[c]); xt[c] = fma(an, k[c], x[c]); }
+            }
             if (unit < a.B) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+                for (int c = 0; c < 13; ++c) { x[c] = fma(a.rk.h6, acc[c], x[c]); __stcs(a.xn + (long)c * a.ld + unit, x[c]); }
                 if (a.status) a.status[unit] = pre | (all_finite13(x) ? 0 : FLAG_NONFINITE);
             }
         }
-        __syncwarp();
-        // pre-step state of this lane's filter of the coming round: fetched one round ahead (the loads fly behind phase B)
-        double xq[13], uq[3];
-        {
-            const int f = lane & 7;
-#pragma unroll
-            for (int c = 0; c < 13; ++c) xq[c] = __ldcg(Xw + c * 32 + f);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) uq[c] = __ldcg(Xw + (13 + c) * 32 + f);
-        }
+        __syncwarp();                               // round 0's tile (written by lanes 0..7) is visible to the warp
 #pragma unroll 1
         for (int r = 0; r < 4; ++r, ++t) {
-            // ---------------- Jacobian at the pre-step state of filters 8 r .. 8 r + 7 -> shared tile --------
-            {
-                const int f = lane & 7;
-                double fdum[13];
-                Rep0Sink sink{Jt + (f >> 2) * C::TILE_S + (f & 3), lane < 8};
-                model_eval<RIGID, true>(a.K, a.K.A, xq, uq, fdum, sink);
-                if (r < 3) {
-#pragma unroll
-                    for (int c = 0; c < 13; ++c) xq[c] = __ldcg(Xw + c * 32 + (r + 1) * 8 + f);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) uq[c] = __ldcg(Xw + (13 + c) * 32 + (r + 1) * 8 + f);
-                }
+            const double* const Tt = Jt + (t & 1) * C::TILE_D;
+            if (r > 0) {                            // the round's Jacobian tile has landed
+                if (t & 1) { mbar_wait(bars + 3, tile_ph1); tile_ph1 ^= 1; }
+                else { mbar_wait(bars + 2, tile_ph0); tile_ph0 ^= 1; }
             }
-            __syncwarp();
             unsigned char* const box = wb + (t & 1) * C::BOX;
             mbar_wait(bars + (t & 1), (t >> 1) & 1);
             // ---------------- phase B: 8 lanes = filter, 2 passes of 4 filters ---------------------------------
+            // Box entry (row, col) of this lane's filter sits at box + (row * 13 + col) * 64 + filter * 8 with the TMA's 64-byte
+            // swizzle (16-byte chunk index ^= address bits 7..8).  The swizzled address is computed from the absolute shared
+            // address (3 integer instructions on the idle ALU pipe) instead of being looked up in a per-lane offset table in
+            // shared memory: 104 of the 406 shared-memory instructions of a pass, and one LDS latency in front of every
+            // product, were table lookups (profiles/r2o ncu source page).
+            // (boxes are 512-byte aligned, so address bits 7..8 are those of the offset)
+            auto sw = [](unsigned o) -> unsigned { return o ^ ((o >> 3) & 0x30u); };
+            auto BX = [&](unsigned o) -> double& { return *reinterpret_cast<double*>(box + sw(o)); };
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {
-                const double* __restrict__ T = Jt + p * C::TILE_S + lu;
-                const unsigned px = p ? 32u : 0u;
+                const double* __restrict__ T = Tt + p * 4 + lu;
+                const unsigned fo = (unsigned)(p * 4 + lu) * 8u;                           // this lane's filter column of the box
+                const unsigned row0 = fo + (unsigned)(r0 * 13) * 64u, row1 = fo + (unsigned)((v1 ? r1 : r0) * 13) * 64u;   // entry (r, 0)
+                const unsigned col0 = fo + (unsigned)r0 * 64u, col1 = fo + (unsigned)(v1 ? r1 : r0) * 64u;                 // entry (0, c)
                 double p0[13], p1[13], n0[13], n1[13];
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of P
-                    const unsigned o = rtab[k * 32] ^ (px | (px << 16));
-                    p0[k] = *reinterpret_cast<const double*>(box + (o & 0xffffu));
-                    p1[k] = v1 ? *reinterpret_cast<const double*>(box + (o >> 16)) : 0.0;
+                    p0[k] = BX(row0 + k * 64u);
+                    p1[k] = v1 ? BX(row1 + k * 64u) : 0.0;
                 }
-                ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+                ekf_jx_times2<ARM, RIGID, 8>(T, p0, p1, n0, n1);
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of Q = P A^T, in place
-                    const unsigned o = rtab[k * 32] ^ (px | (px << 16));
-                    *reinterpret_cast<double*>(box + (o & 0xffffu)) = fma(a.dt, n0[k], p0[k]);
-                    if (v1) *reinterpret_cast<double*>(box + (o >> 16)) = fma(a.dt, n1[k], p1[k]);
+                    BX(row0 + k * 64u) = fma(a.dt, n0[k], p0[k]);
+                    if (v1) BX(row1 + k * 64u) = fma(a.dt, n1[k], p1[k]);
                 }
                 __syncwarp();
                 if (p == 0) {
@@ -1065,20 +1071,19 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                 }
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // columns r0, r1 of Q
-                    const unsigned o = ctab[k * 32] ^ (px | (px << 16));
-                    p0[k] = *reinterpret_cast<const double*>(box + (o & 0xffffu));
-                    p1[k] = v1 ? *reinterpret_cast<const double*>(box + (o >> 16)) : 0.0;
+                    p0[k] = BX(col0 + k * (13 * 64u));
+                    p1[k] = v1 ? BX(col1 + k * (13 * 64u)) : 0.0;
                 }
-                ekf_jx_times2<ARM, RIGID>(T, p0, p1, n0, n1);
+                ekf_jx_times2<ARM, RIGID, 8>(T, p0, p1, n0, n1);
 #pragma unroll
                 for (int i = 0; i < 13; ++i) {          // columns r0, r1 of Pn = A Q + W, in place
-                    const unsigned o = ctab[i * 32] ^ (px | (px << 16));
-                    *reinterpret_cast<double*>(box + (o & 0xffffu)) = fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0];
-                    if (v1) *reinterpret_cast<double*>(box + (o >> 16)) = fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1];
+                    BX(col0 + i * (13 * 64u)) = fma(a.dt, n0[i], p0[i]) + Ws[i * 13 + r0];
+                    if (v1) BX(col1 + i * (13 * 64u)) = fma(a.dt, n1[i], p1[i]) + Ws[i * 13 + r1];
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
+            __syncwarp();                           // every lane is done with the tile and the box of this round
+            if (r < 2) issue_tile(t + 2, r + 2);    // this round's tile buffer is free: the tile of round r + 2 lands a round ahead
             if (lane == 0) {                            // filters >= B are clipped by the tensor map
                 asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                              :: "l"(reinterpret_cast<unsigned long long>(&ta.tmPn)), "r"((int)(g * 32 + r * 8)), "r"(0), "r"(0),

@@ -236,8 +236,9 @@ def compose(orc, sym, dev):
     # k_sens_fused: primal pass (RK4 step) + 4 x (f + J) (the Jacobian pass recomputes f's intermediates) + phase B
     # (phase B: 104 x 16 FMAs per stage for Jx D, and 7 x 8 for the Ju columns -- one FMA per lane of a unit)
     d["RK4_SENS_STEP"] = d["RK4_STEP"] + 4 * d["RHS_JAC"] + 3 * (2 * NNZ_JX * T + 2 * NNZ_JU * 8) + tableau
-    # k_ekf_predict_tma: RK4 step + (f + J) + two SPARSE products  Q = P + dt (P J^T),  Pn = Q + dt (J Q) + W
-    d["EKF_PREDICT"] = d["RK4_STEP"] + d["RHS_JAC"] + 2 * (2 * NNZ_JX * n + 2 * n * n) + n * n
+    # k_ekf_predict_tma: RK4 step whose first stage is the (f + J) evaluation (k1 and the Jacobian share the pre-step point)
+    # + two SPARSE products  Q = P + dt (P J^T),  Pn = Q + dt (J Q) + W
+    d["EKF_PREDICT"] = d["RK4_STEP"] - d["RHS"] + d["RHS_JAC"] + 2 * (2 * NNZ_JX * n + 2 * n * n) + n * n
     d["COLLOC_SCENARIO"] = M * (d["RHS_JAC"] + 19 + 2 * (NNZ_JX + 1) + 2 * (NNZ_JU + 1) + 15) + 165 * 6 * 2 + 165 * 2
     return o, d
 
