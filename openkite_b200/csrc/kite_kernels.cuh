@@ -114,6 +114,15 @@ struct RolloutArgs {
     long index0;
 };
 
+// load flavour of the per-step control stream (read once): __ldg, or ld.global.L1::no_allocate to keep the stream out of L1
+__device__ __forceinline__ double ld_noalloc(const double* p) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+#ifndef KITE_LDU
+#define KITE_LDU __ldg
+#endif
 #ifndef KITE_PF_INSTR
 #define KITE_PF_INSTR "prefetch.global.L2"
 #endif
@@ -204,7 +213,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
             for (int c = 0; c < 3; ++c) uu[c] = __ldg(a.u + (long)c * a.ld + i);
         } else if constexpr (UMODE == 1) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) uu[c] = __ldg(up + (long)c * a.ld);
+            for (int c = 0; c < 3; ++c) uu[c] = KITE_LDU(up + (long)c * a.ld);
         } else if constexpr (UMODE == 2) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) uu[c] = __ldg(up + c);

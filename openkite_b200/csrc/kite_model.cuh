@@ -179,9 +179,9 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     const double ca = xe * irho, sa = v[2] * irho;            // cos/sin(angle of attack)
     // both angles from their (sin, cos) pairs, branch free for any sideslip and any angle of attack (all four
     // quadrants): two interleaved polynomial chains, no division, no libm, no warp divergence (kite_math.cuh)
-    // Table forms of the special functions where the coefficients come from shared memory (identification sweeps): measured
-    // +3.4 % there (shared controls, nothing else on the load path), neutral to -1.2 % on the config-2 kernel, which stays on
-    // the polynomial forms (profiles/r2e_sweep_tables.log)
+    // Angles: table + short series in every kernel (KITE_ANGLE_TABLE, kite_math.cuh: config 2 +1.6 %).  Exponential of the
+    // tether logistic: the 2^(j/32) table form only where the coefficients come from shared memory (identification sweeps:
+    // +1.6 % on top of the angle table there, -0.5 % on the config-2 kernel: profiles/r2e_sweep_tables.log, r2r_sweep.log)
     constexpr bool TAB = std::is_volatile<AC>::value;
     const double ss = asin_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sb, cb);
     const double aoa = atan2_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sa, ca);

@@ -119,6 +119,44 @@ def test_sensitivity_kernel_is_schedule_independent(eng):
             assert torch.equal(ta[:, lo:hi], tc), (lo, hi)
 
 
+def test_sens_rollout_1m_trajectories(eng, oracle):
+    """The north_star shape (RK4 + sensitivity rollouts of >= 1 M trajectories; bench.py's `rk4_sens_rollout` line):
+    1,048,576 trajectories x 10 steps in one launch, 18.9 GB of [Phi | Gamma].  A sample of global indices against the
+    oracle, bitwise re-sharding (the second half as its own call), the semigroup property of the chained sensitivities,
+    and status flags all clear."""
+    B, N, h = 1 << 20, 10, 0.02
+    x0, u = eng.synth_inputs(B, N)
+    st = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    eng.set_status_buffer(st)
+    try:
+        xs, Phi, Gam = eng.sens_rollout(x0, u, h)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_status_buffer(None)
+    assert int(st.abs().sum()) == 0                                        # finite everywhere, no singular evaluation point
+    idx = _sample(np.random.default_rng(11), B, 64)
+    ti = torch.from_numpy(idx).cuda()
+    x0s = aos(x0[:, ti]); us = u[:, :, ti].permute(2, 0, 1).cpu().numpy()
+    rxs, rPhi, rGam = oracle.rk4_sens_rollout(x0s, us, h, nthreads=4)
+    assert_close(xs[:, :, ti].permute(2, 0, 1).cpu().numpy(), rxs, RTOL, what="1M sens rollout states")
+    assert_close(Phi[:, :, ti].permute(2, 0, 1).cpu().numpy().reshape(len(idx), N, 13, 13), rPhi, RTOL, what="1M sens rollout Phi")
+    assert_close(Gam[:, :, ti].permute(2, 0, 1).cpu().numpy().reshape(len(idx), N, 13, 3), rGam, RTOL, what="1M sens rollout Gamma")
+    # re-sharding: the second half as its own call (what rank 1 of 2 would compute) is bitwise the same
+    H = B // 2
+    xs2, Phi2, Gam2 = eng.sens_rollout(x0[:, H:].contiguous(), u[:, :, H:].contiguous(), h)
+    assert torch.equal(xs2, xs[:, :, H:]) and torch.equal(Phi2[N - 1], Phi[N - 1, :, H:]) and torch.equal(Gam2[0], Gam[0, :, H:])
+    del xs2, Phi2, Gam2
+    # semigroup: the product of the step sensitivities is the sensitivity of the whole horizon (finite difference on a slice)
+    S = 4096
+    d = torch.zeros(13, S, dtype=torch.float64, device="cuda"); d[2] = 1e-7
+    xsd, _, _ = eng.sens_rollout((x0[:, :S] + d).contiguous(), u[:, :, :S].contiguous(), h)
+    v = d
+    for k in range(N):
+        v = torch.einsum("ijb,jb->ib", Phi[k, :, :S].reshape(13, 13, S), v)
+    err = (xsd[-1] - xs[-1, :, :S] - v).abs().amax(0)
+    assert float(torch.quantile(err / v.abs().amax(0).clamp_min(1e-12), 0.999)) < 1e-3
+
+
 def test_config4_full_size_collocation(eng, okb, oracle, golden):
     """config 4: 65,536 NMPC scenarios (P = 5, S = 2, nmpf_node scaling): G, dG blocks, cost and gradient."""
     from openkite_b200.collocation import comp_diff_matrix, quad_weights
