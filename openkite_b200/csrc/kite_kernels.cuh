@@ -418,7 +418,7 @@ template <bool ARM> struct SfCfg {
     static constexpr int FIT = (int)((SF_SMEM_MAX - 4096) / SMEM_PER_WARP);
     static constexpr int WARPS = SF_WARPS < FIT ? SF_WARPS : FIT;
     static constexpr size_t SMEM_TILES = SMEM_PER_WARP * WARPS;
-    static constexpr size_t SMEM = SMEM_TILES + 2 * sizeof(unsigned) * 13 * 32;   // + gather table, staging table
+    static constexpr size_t SMEM = SMEM_TILES + sizeof(unsigned) * 13 * 32;       // + gather table
     // TMA output: the [169][8] and [39][8] boxes of a ROUND (both passes) are staged in pass 0's tiles, all four dead once
     // pass 0 has consumed them (bytes from the warp's base, 128-byte aligned).  The [169] box runs over the zero slots of
     // pass 0's stage-1 tile, which are restored after the TMA has read the box.
@@ -484,23 +484,19 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
             goff[i * 32] = (unsigned)(C::at(s0, lu) * 8) | ((unsigned)(C::at(s1, lu) * 8) << 16);
         }
     }
-    // staging table (TMA output): byte offsets, from the warp's base, of row i of this lane's two output columns in the
-    // [169][8] / [39][8] boxes of a round, for pass 0 (pass 1: offset ^ 32), c0 in the low and c1 in the high half.  The
-    // boxes use the TMA's 64-byte swizzle (16-byte chunk index ^= address bits 7..8), so the eight rows of a half-warp
-    // store land in eight different 16-byte bank groups: conflict free instead of 4-way at the dense 64-byte row pitch.
-    unsigned* const soff = reinterpret_cast<unsigned*>(smem_raw + C::SMEM_TILES) + 13 * 32 + lane;
-    if (TMA_OUT && warp == 0) {
-        const unsigned base_abs = (unsigned)__cvta_generic_to_shared(smem_raw);
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            const unsigned log0 = (unsigned)C::BOX_PHI + (unsigned)(i * 13 + c0) * 64u + (unsigned)lu * 8u;
-            const unsigned log1 = (c1 < 13) ? (unsigned)C::BOX_PHI + (unsigned)(i * 13 + c1) * 64u + (unsigned)lu * 8u
-                                            : (unsigned)C::BOX_GAM + (unsigned)(i * 3 + c1 - 13) * 64u + (unsigned)lu * 8u;
-            const unsigned ph0 = log0 ^ ((((base_abs + log0) >> 7) & 3u) << 4);
-            const unsigned ph1 = log1 ^ ((((base_abs + log1) >> 7) & 3u) << 4);
-            soff[i * 32] = ph0 | (ph1 << 16);
-        }
-    }
+    // staging (TMA output): row i of this lane's two output columns goes to the [169][8] / [39][8] boxes of the round, which
+    // use the TMA's 64-byte swizzle (16-byte chunk index ^= address bits 7..8), so the eight rows of a half-warp store land in
+    // eight different 16-byte bank groups: conflict free instead of 4-way at the dense 64-byte row pitch.  The swizzled
+    // offset is COMPUTED (box row R = i * stride + column: chunk bits = (8 R + 16 (box address >> 7)) & 0x30, three integer
+    // instructions on the idle ALU pipe); round 2 looked it up in a per-lane table in shared memory, and the stores waited
+    // on those lookups for 10 % of the kernel's time (profiles/r2t ncu source page: short_scoreboard on the LOP3 after the LDS).
+    const unsigned wb_abs = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(warp * C::SMEM_PER_WARP);
+    const bool gam1 = c1 >= 13;                     // lanes 5..7: the second column is a column of Gamma
+    const unsigned col1 = gam1 ? c1 - 13 : c1;
+    const unsigned box1 = gam1 ? (unsigned)C::BOX_GAM : (unsigned)C::BOX_PHI;
+    const unsigned sA0 = (unsigned)C::BOX_PHI + (unsigned)c0 * 64u, sA1 = box1 + col1 * 64u;             // offset of row 0 of the column
+    const unsigned sE0 = 8u * c0 + (((wb_abs + (unsigned)C::BOX_PHI) >> 7) << 4), sE1 = 8u * col1 + (((wb_abs + box1) >> 7) << 4);
+    const unsigned sR1 = gam1 ? 3u : 13u;           // box rows per matrix row
     __syncthreads();
     const double h6 = a.h / 6.0, hh = 0.5 * a.h;
     // Groups are claimed from a global counter instead of a fixed stride: warps that share a scheduler run at different
@@ -682,12 +678,13 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                     unsigned char* const bphi = wb + C::BOX_PHI;
                     unsigned char* const bgam = wb + C::BOX_GAM;
                     if (p == 0) __syncwarp();           // every lane is done with pass 0's tiles (the box lies over them)
-                    const unsigned px = p ? 32u : 0u;
+                    const unsigned fo = (unsigned)lu * 8u + (p ? 32u : 0u);     // this lane's unit within the 64-byte row
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
-                        const unsigned o = soff[i * 32] ^ (px | (px << 16));
-                        *reinterpret_cast<double*>(wb + (o & 0xffffu)) = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
-                        *reinterpret_cast<double*>(wb + (o >> 16)) = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
+                        const unsigned o0 = sA0 + (unsigned)i * 832u + (((sE0 + (unsigned)i * 104u) & 0x30u) ^ fo);
+                        const unsigned o1 = sA1 + (unsigned)i * (sR1 * 64u) + (((sE1 + (unsigned)i * (sR1 * 8u)) & 0x30u) ^ fo);
+                        *reinterpret_cast<double*>(wb + o0) = fma(h6, A0[i], (i == c0) ? 1.0 : 0.0);
+                        *reinterpret_cast<double*>(wb + o1) = fma(h6, A1[i], (i == c1) ? 1.0 : 0.0);
                     }
                     if (p == 1) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -905,6 +902,18 @@ struct EkfTmaArgs {
     EkfArgs e;
     double* Jw;                       // scratch: [resident warp][4 rounds][NS slots][8 filters]
 };
+#ifndef KITE_EKF_PFX
+#define KITE_EKF_PFX 0
+#endif
+#ifndef KITE_EKF_NOTMA
+#define KITE_EKF_NOTMA 0        // experiment: no covariance traffic at all (results are garbage; times the compute alone)
+#endif
+#ifndef KITE_EKF_DIRECT_P
+#define KITE_EKF_DIRECT_P 0     // experiment: rows of P straight from global memory into registers, one pass ahead; TMA stores only
+#endif
+#ifndef KITE_EKF_LOAD_AT
+#define KITE_EKF_LOAD_AT 0
+#endif
 template <bool ARM> struct EtCfg {
     static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM - 7;          // state-Jacobian slots (no Ju)
     static constexpr int TILE_D = NS * 8;                                         // doubles per round tile [slot][8 filters]
@@ -968,7 +977,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
 
     // box of the warp's round `t` (filters first .. first + 7) -> buffer t & 1, one TMA tensor load issued by lane 0
     auto issue_load = [&](unsigned t, long first) {
-        if (lane == 0) {
+        if (!KITE_EKF_NOTMA && !KITE_EKF_DIRECT_P && lane == 0) {
             const unsigned bar = smem_u32(bars + (t & 1));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::BOX_BYTES) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -996,6 +1005,18 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
     if (g < ngroups) issue_load(0, g * 32);
     while (g < ngroups) {
         const long g_next = claim_group();
+#if KITE_EKF_PFX
+        if (g_next < ngroups) {                     // next group's state and control lines -> L2 while this group computes
+            const long un = g_next * 32 + lane;
+            const long pi = un < a.B ? un : a.B - 1;
+#pragma unroll
+            for (int c = 0; c < 13; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.x + (long)c * a.ld + pi));
+            if (a.u) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.u + (long)c * a.ld + pi));
+            }
+        }
+#endif
         // ---------------- step 1: lane = filter: Jacobian + k1 at the pre-step state, then the rest of the RK4 step ------
         {
             const long unit = g * 32 + lane;
@@ -1034,6 +1055,19 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             }
         }
         __syncwarp();                               // round 0's tile (written by lanes 0..7) is visible to the warp
+#if KITE_EKF_DIRECT_P
+        double pn0[13], pn1[13];
+        auto load_rows = [&](int pass) {            // rows r0, r1 of P of the 4 filters of a pass
+            const long unit = g * 32 + pass * 4 + lu;
+            const long ui = unit < a.B ? unit : a.B - 1;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                pn0[k] = __ldcs(a.P + (long)(r0 * 13 + k) * a.ld + ui);
+                pn1[k] = v1 ? __ldcs(a.P + (long)(r1 * 13 + k) * a.ld + ui) : 0.0;
+            }
+        };
+        load_rows(0);
+#endif
 #pragma unroll 1
         for (int r = 0; r < 4; ++r, ++t) {
             const double* const Tt = Jt + (t & 1) * C::TILE_D;
@@ -1042,7 +1076,11 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                 else { mbar_wait(bars + 2, tile_ph0); tile_ph0 ^= 1; }
             }
             unsigned char* const box = wb + (t & 1) * C::BOX;
-            mbar_wait(bars + (t & 1), (t >> 1) & 1);
+            if (!KITE_EKF_NOTMA && !KITE_EKF_DIRECT_P) mbar_wait(bars + (t & 1), (t >> 1) & 1);
+#if KITE_EKF_DIRECT_P
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of round t - 2 has left this box
+            __syncwarp();
+#endif
             // ---------------- phase B: 8 lanes = filter, 2 passes of 4 filters ---------------------------------
             // Box entry (row, col) of this lane's filter sits at box + (row * 13 + col) * 64 + filter * 8 with the TMA's 64-byte
             // swizzle (16-byte chunk index ^= address bits 7..8).  The swizzled address is computed from the absolute shared
@@ -1052,18 +1090,32 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             // (boxes are 512-byte aligned, so address bits 7..8 are those of the offset)
             auto sw = [](unsigned o) -> unsigned { return o ^ ((o >> 3) & 0x30u); };
             auto BX = [&](unsigned o) -> double& { return *reinterpret_cast<double*>(box + sw(o)); };
+            auto next_box = [&](int r) {
+                // half a round after the previous round's store was issued: its buffer has been read out, the next
+                // round's box may land in it (next round of this group, or round 0 of the next group)
+                const long nfirst = (r < 3) ? g * 32 + (r + 1) * 8 : g_next * 32;
+                if (!KITE_EKF_DIRECT_P && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (r < 3 || g_next < ngroups) issue_load(t + 1, nfirst);
+            };
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {
                 const double* __restrict__ T = Tt + p * 4 + lu;
+                if (KITE_EKF_LOAD_AT == 1 && p == 1) next_box(r);
                 const unsigned fo = (unsigned)(p * 4 + lu) * 8u;                           // this lane's filter column of the box
                 const unsigned row0 = fo + (unsigned)(r0 * 13) * 64u, row1 = fo + (unsigned)((v1 ? r1 : r0) * 13) * 64u;   // entry (r, 0)
                 const unsigned col0 = fo + (unsigned)r0 * 64u, col1 = fo + (unsigned)(v1 ? r1 : r0) * 64u;                 // entry (0, c)
                 double p0[13], p1[13], n0[13], n1[13];
+#if KITE_EKF_DIRECT_P
+#pragma unroll
+                for (int k = 0; k < 13; ++k) { p0[k] = pn0[k]; p1[k] = pn1[k]; }
+                if (r * 2 + p < 7) load_rows(r * 2 + p + 1);
+#else
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of P
                     p0[k] = BX(row0 + k * 64u);
                     p1[k] = v1 ? BX(row1 + k * 64u) : 0.0;
                 }
+#endif
                 ekf_jx_times2<ARM, RIGID, 8>(T, p0, p1, n0, n1);
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of Q = P A^T, in place
@@ -1071,13 +1123,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                     if (v1) BX(row1 + k * 64u) = fma(a.dt, n1[k], p1[k]);
                 }
                 __syncwarp();
-                if (p == 0) {
-                    // half a round after the previous round's store was issued: its buffer has been read out, the next
-                    // round's box may land in it (next round of this group, or round 0 of the next group)
-                    const long nfirst = (r < 3) ? g * 32 + (r + 1) * 8 : g_next * 32;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    if (r < 3 || g_next < ngroups) issue_load(t + 1, nfirst);
-                }
+                if (KITE_EKF_LOAD_AT != 1 && p == KITE_EKF_LOAD_AT / 2) next_box(r);
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // columns r0, r1 of Q
                     p0[k] = BX(col0 + k * (13 * 64u));
@@ -1093,7 +1139,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();                           // every lane is done with the tile and the box of this round
             if (r < 2) issue_tile(t + 2, r + 2);    // this round's tile buffer is free: the tile of round r + 2 lands a round ahead
-            if (lane == 0) {                            // filters >= B are clipped by the tensor map
+            if (KITE_EKF_NOTMA != 1 && lane == 0) {                            // filters >= B are clipped by the tensor map
                 asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                              :: "l"(reinterpret_cast<unsigned long long>(&ta.tmPn)), "r"((int)(g * 32 + r * 8)), "r"(0), "r"(0),
                                 "r"(smem_u32(box)) : "memory");
