@@ -902,17 +902,8 @@ struct EkfTmaArgs {
     EkfArgs e;
     double* Jw;                       // scratch: [resident warp][4 rounds][NS slots][8 filters]
 };
-#ifndef KITE_EKF_PFX
-#define KITE_EKF_PFX 0
-#endif
 #ifndef KITE_EKF_NOTMA
-#define KITE_EKF_NOTMA 0        // experiment: no covariance traffic at all (results are garbage; times the compute alone)
-#endif
-#ifndef KITE_EKF_DIRECT_P
-#define KITE_EKF_DIRECT_P 0     // experiment: rows of P straight from global memory into registers, one pass ahead; TMA stores only
-#endif
-#ifndef KITE_EKF_LOAD_AT
-#define KITE_EKF_LOAD_AT 0
+#define KITE_EKF_NOTMA 0        // developer timing switch (results are garbage): 1 = no covariance traffic at all, 2 = no loads, stores kept
 #endif
 template <bool ARM> struct EtCfg {
     static constexpr int NS = ARM ? SENS_SLOTS : SENS_SLOTS_NOARM - 7;          // state-Jacobian slots (no Ju)
@@ -977,7 +968,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
 
     // box of the warp's round `t` (filters first .. first + 7) -> buffer t & 1, one TMA tensor load issued by lane 0
     auto issue_load = [&](unsigned t, long first) {
-        if (!KITE_EKF_NOTMA && !KITE_EKF_DIRECT_P && lane == 0) {
+        if (!KITE_EKF_NOTMA && lane == 0) {
             const unsigned bar = smem_u32(bars + (t & 1));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C::BOX_BYTES) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -1005,18 +996,6 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
     if (g < ngroups) issue_load(0, g * 32);
     while (g < ngroups) {
         const long g_next = claim_group();
-#if KITE_EKF_PFX
-        if (g_next < ngroups) {                     // next group's state and control lines -> L2 while this group computes
-            const long un = g_next * 32 + lane;
-            const long pi = un < a.B ? un : a.B - 1;
-#pragma unroll
-            for (int c = 0; c < 13; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.x + (long)c * a.ld + pi));
-            if (a.u) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.u + (long)c * a.ld + pi));
-            }
-        }
-#endif
         // ---------------- step 1: lane = filter: Jacobian + k1 at the pre-step state, then the rest of the RK4 step ------
         {
             const long unit = g * 32 + lane;
@@ -1055,19 +1034,6 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
             }
         }
         __syncwarp();                               // round 0's tile (written by lanes 0..7) is visible to the warp
-#if KITE_EKF_DIRECT_P
-        double pn0[13], pn1[13];
-        auto load_rows = [&](int pass) {            // rows r0, r1 of P of the 4 filters of a pass
-            const long unit = g * 32 + pass * 4 + lu;
-            const long ui = unit < a.B ? unit : a.B - 1;
-#pragma unroll
-            for (int k = 0; k < 13; ++k) {
-                pn0[k] = __ldcs(a.P + (long)(r0 * 13 + k) * a.ld + ui);
-                pn1[k] = v1 ? __ldcs(a.P + (long)(r1 * 13 + k) * a.ld + ui) : 0.0;
-            }
-        };
-        load_rows(0);
-#endif
 #pragma unroll 1
         for (int r = 0; r < 4; ++r, ++t) {
             const double* const Tt = Jt + (t & 1) * C::TILE_D;
@@ -1076,11 +1042,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                 else { mbar_wait(bars + 2, tile_ph0); tile_ph0 ^= 1; }
             }
             unsigned char* const box = wb + (t & 1) * C::BOX;
-            if (!KITE_EKF_NOTMA && !KITE_EKF_DIRECT_P) mbar_wait(bars + (t & 1), (t >> 1) & 1);
-#if KITE_EKF_DIRECT_P
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of round t - 2 has left this box
-            __syncwarp();
-#endif
+            if (!KITE_EKF_NOTMA) mbar_wait(bars + (t & 1), (t >> 1) & 1);
             // ---------------- phase B: 8 lanes = filter, 2 passes of 4 filters ---------------------------------
             // Box entry (row, col) of this lane's filter sits at box + (row * 13 + col) * 64 + filter * 8 with the TMA's 64-byte
             // swizzle (16-byte chunk index ^= address bits 7..8).  The swizzled address is computed from the absolute shared
@@ -1094,28 +1056,21 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                 // half a round after the previous round's store was issued: its buffer has been read out, the next
                 // round's box may land in it (next round of this group, or round 0 of the next group)
                 const long nfirst = (r < 3) ? g * 32 + (r + 1) * 8 : g_next * 32;
-                if (!KITE_EKF_DIRECT_P && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 if (r < 3 || g_next < ngroups) issue_load(t + 1, nfirst);
             };
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {
                 const double* __restrict__ T = Tt + p * 4 + lu;
-                if (KITE_EKF_LOAD_AT == 1 && p == 1) next_box(r);
                 const unsigned fo = (unsigned)(p * 4 + lu) * 8u;                           // this lane's filter column of the box
                 const unsigned row0 = fo + (unsigned)(r0 * 13) * 64u, row1 = fo + (unsigned)((v1 ? r1 : r0) * 13) * 64u;   // entry (r, 0)
                 const unsigned col0 = fo + (unsigned)r0 * 64u, col1 = fo + (unsigned)(v1 ? r1 : r0) * 64u;                 // entry (0, c)
                 double p0[13], p1[13], n0[13], n1[13];
-#if KITE_EKF_DIRECT_P
-#pragma unroll
-                for (int k = 0; k < 13; ++k) { p0[k] = pn0[k]; p1[k] = pn1[k]; }
-                if (r * 2 + p < 7) load_rows(r * 2 + p + 1);
-#else
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of P
                     p0[k] = BX(row0 + k * 64u);
                     p1[k] = v1 ? BX(row1 + k * 64u) : 0.0;
                 }
-#endif
                 ekf_jx_times2<ARM, RIGID, 8>(T, p0, p1, n0, n1);
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // rows r0, r1 of Q = P A^T, in place
@@ -1123,7 +1078,7 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
                     if (v1) BX(row1 + k * 64u) = fma(a.dt, n1[k], p1[k]);
                 }
                 __syncwarp();
-                if (KITE_EKF_LOAD_AT != 1 && p == KITE_EKF_LOAD_AT / 2) next_box(r);
+                if (p == 0) next_box(r);
 #pragma unroll
                 for (int k = 0; k < 13; ++k) {          // columns r0, r1 of Q
                     p0[k] = BX(col0 + k * (13 * 64u));
