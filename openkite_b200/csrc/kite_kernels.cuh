@@ -1294,6 +1294,25 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
     const long s = (long)blockIdx.x * 32 + lane;
     const int M = a.M;
     double g2 = 0.0;
+    {
+        // Pull the CTA's whole block of decision variables (19 M rows x 32 scenarios, 2 lines per row) towards the SM before
+        // anything depends on it: a thread otherwise meets a first-touch DRAM miss at its own node AND in every column of its
+        // (compD (x) I) X row block (the neighbour nodes' rows: dependent misses, 36 % of the sparse kernel's time,
+        // profiles/r2v ncu source page).  128 threads, <= 4 prefetches each, no registers held.
+        const int nlines = 2 * 19 * M;
+        const long s0 = (long)blockIdx.x * 32;
+        for (int t = ky * 32 + lane; t < nlines; t += 32 * NPB) {
+            const long col = s0 + (t & 1) * 16;
+            if (col < a.B) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.z + (long)(t >> 1) * a.ld + col));
+        }
+    }
+    // shared coefficients with the tether-arm entries (FMT 2): read from shared memory as well -- as uniform operands from the
+    // constant bank that instantiation alone spilled (88 B); one record per CTA, broadcast loads
+    constexpr bool COEF_SH = !PERCOEF && FMT == 2;
+    if constexpr (COEF_SH) {
+        if (lane == 0 && ky == 0) coef_sh[0] = a.K.A;
+        __syncthreads();
+    }
     if (s < a.B) {
         if constexpr (PERCOEF) {
             AeroCoef At;
@@ -1350,6 +1369,7 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
                 constexpr int NNZ = ARM ? COLLOC_NNZ_ARM : COLLOC_NNZ_NOARM;
                 CollocSparseSink<ARM> sink{a.JX + (long)(k * NNZ) * a.ld + s, a.ld, a.sx, a.isx, a.isu};
                 if constexpr (PERCOEF) kite_eval<true>(a.K, Av, x, u, f, sink);
+                else if constexpr (COEF_SH) kite_eval<true>(a.K, reinterpret_cast<const volatile AeroCoefPlain&>(coef_sh[0]), x, u, f, sink);
                 else kite_eval<true>(a.K, a.K.A, x, u, f, sink);
                 sink.jv[(long)(ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[13][14] * a.ld] = a.sx[13] * a.isx[14];
                 sink.jv[(long)(ARM ? COLLOC_TAB_ARM : COLLOC_TAB_NOARM).slot[14][18] * a.ld] = a.sx[14] * a.isu[3];
@@ -1365,11 +1385,17 @@ __global__ void __launch_bounds__(32 * NPB) k_colloc_eval(const __grid_constant_
             for (int c = 0; c < 15; ++c) acc[c] = 0.0;
             if (a.cd_compact) {                    // (uniform) the row's non-zeros come from the constant bank: the 15 loads of
                 const int nz = a.cd_nz[k];         // every column are independent of everything but the column index
-                for (int t = 0; t < nz; ++t) {
+                auto column = [&](int t) {
                     const double dkl = a.cd_val[k][t];
                     const double* zl = a.z + (long)(a.cd_col[k][t] * 15) * a.ld + s;
 #pragma unroll
                     for (int c = 0; c < 15; ++c) acc[c] = fma(dkl, __ldg(zl + (long)c * a.ld), acc[c]);
+                };
+                if constexpr (FMT == 0 || FMT == 2) {   // dense blocks are HBM-write bound; there and with the tether-arm entries the unrolled loop spills
+                    for (int t = 0; t < nz; ++t) column(t);
+                } else {                           // two columns' loads in flight (the rows sit in L2 by now): 0.183 -> 0.170 ms sparse
+#pragma unroll 2
+                    for (int t = 0; t < nz; ++t) column(t);
                 }
             } else {
                 for (int l = 0; l < M; ++l) {

@@ -35,6 +35,13 @@ struct AeroCoef {
     double CLde, CYdr, Cmde, Cndr, Cldr;
 };
 
+// Which coefficient types select the table-driven exponential (kite_eval_c): volatile AeroCoef (identification sweeps, per-
+// trajectory records in shared memory) does; AeroCoefPlain is the same record read from shared memory WITHOUT changing the
+// arithmetic -- for kernels whose results must stay bitwise equal to the constant-bank instantiations (collocation, FMT 2).
+struct AeroCoefPlain : AeroCoef {};
+template <class AC> struct exp_table_for : std::is_volatile<AC> {};
+template <> struct exp_table_for<volatile AeroCoefPlain> : std::false_type {};
+
 struct KiteConsts {
     AeroCoef A;              // nominal coefficients (from kite_params)
     double eps;              // 1e-4 standard model (kite.cpp:200-201), 0 identification model (:451-452)
@@ -182,7 +189,7 @@ __device__ __forceinline__ void kite_eval_c(const KiteConsts& K, const AC& A, co
     // Angles: table + short series in every kernel (KITE_ANGLE_TABLE, kite_math.cuh: config 2 +1.6 %).  Exponential of the
     // tether logistic: the 2^(j/32) table form only where the coefficients come from shared memory (identification sweeps:
     // +1.6 % on top of the angle table there, -0.5 % on the config-2 kernel: profiles/r2e_sweep_tables.log, r2r_sweep.log)
-    constexpr bool TAB = std::is_volatile<AC>::value;
+    constexpr bool TAB = exp_table_for<AC>::value;
     const double ss = asin_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sb, cb);
     const double aoa = atan2_sc<TAB || (KITE_ANGLE_TABLE != 0)>(sa, ca);
     const double qS = K.cqS * V2;
