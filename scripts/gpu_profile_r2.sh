@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Run on the GPU box (via gpurun): launch list of the default bench + full ncu captures of the dominant kernels at the
-# benchmark's own sizes.  Usage: bash scripts/gpu_profile_r2.sh <tag> [kernels...]   (kernels: rollout idsweep sens sensroll ekf colloc)
+# benchmark's own sizes.  Usage: bash scripts/gpu_profile_r2.sh <tag> [kernels...]   (kernels: rollout idsweep sens sensroll ekf colloc collocsp)
 TAG=${1:-r2}; shift
 KS=${@:-rollout idsweep sens sensroll ekf}
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
@@ -18,6 +18,7 @@ for k in $KS; do
     sens)     cap sens 'k_sens_fused' 8 ;;                   # then the single steps
     ekf)      cap ekf 'k_ekf_predict' 2 ;;
     colloc)   cap colloc 'k_colloc_eval' 2 ;;
+    collocsp) cap collocsp 'k_colloc_eval' 10 ;;             # launches 0-7 = dense blocks (3 warm-up + 5 timed), then the sparse format
   esac
 done
 ls -la gpurun_out/ | grep $TAG
