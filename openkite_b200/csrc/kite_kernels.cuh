@@ -1115,8 +1115,13 @@ __global__ void __launch_bounds__(EtCfg<ARM>::WARPS * 32, 1) k_ekf_predict_tma(c
 // reads of column c, and K only needs columns 6..12 BEFORE any write).  What made the first in-place version slow
 // (1.65 ms per 1 M filters against 1.27 ms for out-of-place + copy back) was not the missing read-only path but ordering:
 // with loads and stores on the same buffer the compiler may not hoist a load above an earlier store, so
-// "load, 7 FMAs, store" per entry became 169 dependent memory round trips.  Here each column's 20 loads are issued in
-// one batch, one column AHEAD of the stores of the previous column, and the state update is one batch at the end.
+// "load, 7 FMAs, store" per entry became 169 dependent memory round trips.  Here the loads of a column PAIR (26, which
+// contain (H P) of the pair: rows 6..12 of the columns themselves) are issued in one batch, one pair AHEAD of the stores of
+// the previous pair, the pair after that is pulled into L2 by register-free prefetches, every gain entry read from shared
+// memory serves two columns, four rows of K are in flight at once, and the state update is one batch at the end.  The
+// kernel is latency bound at 8 warps per SM (the gain's 832 B of shared memory per filter cap the occupancy, and the
+// alternative -- M = S^-1 (H P) in registers next to S^-1 -- needs the same 196+ registers): round 2, 0.88 -> 0.75 ms per
+// 1 M filters (profiles/r2v_ekf_update_*.log).
 struct EkfUpdArgs {
     long B, ld;
     const double* z; double* P; double* x;
@@ -1124,6 +1129,7 @@ struct EkfUpdArgs {
     int32_t* status;         // [ld] per-filter flag (non-finite updated state: singular innovation covariance) or null
 };
 constexpr int EKFU_BLOCK = 128;
+constexpr int EKFU_KUNROLL = 4;      // rows of K in flight: 28 loads instead of 7 between dependent DRAM round trips (0.88 -> 0.81 ms)
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_constant__ EkfUpdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1155,7 +1161,7 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
     double y[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) y[k] = __ldg(a.z + (long)k * ld + i) - a.x[(long)(6 + k) * ld + i];
-#pragma unroll 1
+#pragma unroll EKFU_KUNROLL
     for (int r = 0; r < 13; ++r) {                 // K row r = P[r][6:13] S^-1; state increment (no global store in this loop)
         double pk[7];
 #pragma unroll
@@ -1179,31 +1185,47 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
         for (int r = 0; r < 13; ++r) { xv[r] += Ks[(91 + r) * EKFU_BLOCK]; a.x[(long)r * ld + i] = xv[r]; }
         if (a.status) a.status[i] = all_finite13(xv) ? 0 : FLAG_NONFINITE;
     }
-    // P[:, c] <- P[:, c] - K (H P)[:, c], column by column; column c + 1 is loaded before column c is stored
-    double hp[7], pv[13], hq[7], pq[13];
+    // P[:, c] <- P[:, c] - K (H P)[:, c], TWO columns per pass: every gain entry read from shared memory serves both, the next
+    // pair's 26 loads fly behind this pair's FMAs, and the pair after that is pulled into L2 (register free).  (H P)[:, c] is
+    // rows 6..12 of column c itself: no separate loads.  Column 13 does not exist: the last pass handles column 12 alone.
+    double pv[2][13], pq[2][13];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) hp[k] = P[(long)((6 + k) * 13) * ld];
-#pragma unroll
-    for (int r = 0; r < 13; ++r) pv[r] = P[(long)(r * 13) * ld];
+    for (int r = 0; r < 13; ++r) { pv[0][r] = P[(long)(r * 13) * ld]; pv[1][r] = P[(long)(r * 13 + 1) * ld]; }
 #pragma unroll 1
-    for (int c = 0; c < 13; ++c) {
-        if (c < 12) {
+    for (int c = 0; c < 13; c += 2) {
+        if (c + 4 < 13 && (threadIdx.x & 15) == 0) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) hq[k] = P[(long)((6 + k) * 13 + c + 1) * ld];
+            for (int r = 0; r < 13; ++r) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(P + (long)(r * 13 + c + 4) * ld));
+                if (c + 5 < 13) asm volatile("prefetch.global.L2 [%0];" :: "l"(P + (long)(r * 13 + c + 5) * ld));
+            }
+        }
+        if (c + 2 < 13) {
 #pragma unroll
-            for (int r = 0; r < 13; ++r) pq[r] = P[(long)(r * 13 + c + 1) * ld];
+            for (int r = 0; r < 13; ++r) {
+                pq[0][r] = P[(long)(r * 13 + c + 2) * ld];
+                pq[1][r] = (c + 3 < 13) ? P[(long)(r * 13 + c + 3) * ld] : 0.0;
+            }
+        }
+        double o0[13], o1[13];
+#pragma unroll
+        for (int r = 0; r < 13; ++r) {
+            double v0 = pv[0][r], v1 = pv[1][r];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const double kk = Ks[(r * 7 + k) * EKFU_BLOCK];
+                v0 = fma(-kk, pv[0][6 + k], v0);
+                v1 = fma(-kk, pv[1][6 + k], v1);
+            }
+            o0[r] = v0; o1[r] = v1;
         }
 #pragma unroll
         for (int r = 0; r < 13; ++r) {
-            double v = pv[r];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) v = fma(-Ks[(r * 7 + k) * EKFU_BLOCK], hp[k], v);
-            P[(long)(r * 13 + c) * ld] = v;
+            P[(long)(r * 13 + c) * ld] = o0[r];
+            if (c + 1 < 13) P[(long)(r * 13 + c + 1) * ld] = o1[r];
         }
 #pragma unroll
-        for (int k = 0; k < 7; ++k) hp[k] = hq[k];
-#pragma unroll
-        for (int r = 0; r < 13; ++r) pv[r] = pq[r];
+        for (int r = 0; r < 13; ++r) { pv[0][r] = pq[0][r]; pv[1][r] = pq[1][r]; }
     }
 }
 
