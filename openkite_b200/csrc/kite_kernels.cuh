@@ -146,6 +146,23 @@ constexpr size_t rollout_smem_bytes(bool percoef) {
     return (percoef ? sizeof(AeroCoef) * ROLLOUT_BLOCK : 0) + (KITE_ROLLOUT_SMEM_STATE ? sizeof(double) * 26 * ROLLOUT_BLOCK : 0);
 }
 
+// Per-warp scratch lines that are written and re-read within microseconds (stage states of the sensitivity kernel, Jacobian
+// tiles of the EKF predict): L2 only, lowest eviction priority class "evict_last", so that the streaming output (which passes
+// through the same L2) does not push the dirty lines out to HBM between the write and the read.
+__device__ __forceinline__ unsigned long long scratch_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));     // pure: the compiler may re-materialise it
+    return pol;
+}
+__device__ __forceinline__ void st_scratch(double* p, double v) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(scratch_policy()) : "memory");
+}
+__device__ __forceinline__ double ld_scratch(const double* p) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(scratch_policy()) : "memory");
+    return v;
+}
+
 // Global thread index from the special registers, opaque to the optimiser: the rollout recomputes it after the time loop
 // instead of keeping 2 registers alive (or spilled) across the whole horizon.
 __device__ __forceinline__ long fresh_thread_index() {
@@ -544,12 +561,12 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
 #pragma unroll
             for (int c = 0; c < 3; ++c) u[c] = RIGID ? 0.0 : __ldcs(uin + (long)c * a.ld + ui);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) __stcg(Sw + (13 + c) * 32 + lane, u[c]);     // (after ALL loads: may-alias stores serialise them)
+            for (int c = 0; c < 3; ++c) st_scratch(Sw + (13 + c) * 32 + lane, u[c]);     // (after ALL loads: may-alias stores serialise them)
             NoSink ns;
 #pragma unroll 1
             for (int st = 0; st < 4; ++st) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcg(Sw + (st * 16 + c) * 32 + lane, xt[c]);
+                for (int c = 0; c < 13; ++c) st_scratch(Sw + (st * 16 + c) * 32 + lane, xt[c]);
                 model_eval<RIGID, false>(a.K, a.K.A, xt, u, k, ns);
                 const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
                 const double an = (st == 2) ? a.h : hh;
@@ -583,9 +600,9 @@ __global__ void __launch_bounds__(SfCfg<ARM>::WARPS * 32, 1) k_sens_fused(const 
                 const int u8 = lane & 7, s = lane >> 3;
                 double xt[13], u[3], k[13];
 #pragma unroll
-                for (int c = 0; c < 13; ++c) xt[c] = __ldcg(Sw + (s * 16 + c) * 32 + r * 8 + u8);
+                for (int c = 0; c < 13; ++c) xt[c] = ld_scratch(Sw + (s * 16 + c) * 32 + r * 8 + u8);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) u[c] = __ldcg(Sw + (13 + c) * 32 + r * 8 + u8);
+                for (int c = 0; c < 3; ++c) u[c] = ld_scratch(Sw + (13 + c) * 32 + r * 8 + u8);
                 StageSink sink{tile + (u8 >> 2) * C::PASS_S + s * C::TILE_S + C::at(0, u8 & 3)};
                 if (TMA_OUT) {                          // the previous round's output boxes have left the tiles
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -928,7 +945,7 @@ struct EkfTileSink {    // state-Jacobian slot s of this lane's filter: scratch 
     double* g;          // &Jw[lane / 8][0][lane % 8]
     double* sh;         // &tile0[0][lane] for lanes 0..7, null otherwise
     __device__ __forceinline__ void jx(int i, int j, double v) const {
-        __stcg(g + SENS_TAB.jx[i][j] * 8, v);
+        st_scratch(g + SENS_TAB.jx[i][j] * 8, v);
         if (sh) sh[SENS_TAB.jx[i][j] * 8] = v;
     }
     __device__ __forceinline__ void ju(int, int, double) const {}
