@@ -212,11 +212,9 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
     for (int c = 0; c < 13; ++c) xs[c * ROLLOUT_BLOCK] = x[c];
 #endif
 
-    // Controls of step k.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 2 are pulled into
-    // L2 by a register-free prefetch while step k computes, and the (then short-latency) load itself happens at the top
-    // of the step -- holding the next step's controls in registers across the step costs 6 registers the RHS needs
-    // (measured: 61.5 % instead of 65.0 % of FP64 peak, profiles/r1u).
-    // Loop state is kept small on purpose (the RHS leaves no spare registers): a 32-bit step counter and ONE running pointer
+    // Controls.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 3 are pulled into L2 by a
+    // register-free prefetch, and the (then short-latency) loads of step k + 1 are issued at the top of step k (below).
+    // Loop state is kept small on purpose (the RHS leaves few spare registers): a 32-bit step counter and ONE running pointer
     // per stream instead of 64-bit index arithmetic per step.
     const int N = (int)a.N;                         // < 2^31 (checked by the host)
     unsigned lane_id;
@@ -243,19 +241,29 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
     const double Qc[13] = {1e3, 1e2, 1e2, 1e2, 1e2, 1e2, 1e1, 1e1, 1e2, 1e2, 1e2, 1e2, 1e2};  // kite_identification_test.cpp:193
     const double* yp = a.y;
     int next_save = (int)a.save_every;
+    // Controls of step k + 1 are loaded at the TOP of step k and fly behind its arithmetic (three registers pairs; the lines
+    // were pulled into L2 two steps earlier).  Round 1 rejected this (61.5 % against 65.0 %) because the kernel spilled;
+    // spill free (and still spill free at a 152-register cap) it is worth 1.5 %: 80.05 -> 78.85 ms (profiles/r2w_sweep_ureg.log).
+    double un[3] = {0.0, 0.0, 0.0};
+    if constexpr (UMODE == 1) { load_u(0, un); up += ustep; }
     for (int k = 0; k < N; ++k) {
-        if constexpr (UMODE != 0) {
-            load_u(k, u);
-            if constexpr (UMODE == 1) {
-                if (pf_lane && k + 2 < N) {                          // one prefetch per 128-byte line
+        if constexpr (UMODE == 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = un[c];
+            if (k + 1 < N) {
+                load_u(k + 1, un);
+                if (pf_lane && k + 3 < N) {                          // one prefetch per 128-byte line, two steps ahead of the load
                     const double* pf = up + 2 * ustep;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) asm volatile(KITE_PF_INSTR " [%0];" :: "l"(pf + (long)c * a.ld));
                 }
                 up += ustep;
-            } else if constexpr (UMODE == 2) {
-                up += 3;
             }
+        } else if constexpr (UMODE == 2) {           // shared log: every thread reads the same three words (L1 broadcast hits)
+            load_u(k, u);
+            up += 3;
+        } else if constexpr (UMODE == 3) {
+            load_u(k, u);
         }
 #if KITE_ROLLOUT_SMEM_STATE
         rk4_step_sm<RIGID, ROLLOUT_BLOCK>(a.K, A, xs, as, u, a.rk);
