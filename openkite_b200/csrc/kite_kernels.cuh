@@ -123,9 +123,6 @@ __device__ __forceinline__ double ld_noalloc(const double* p) {
 #ifndef KITE_LDU
 #define KITE_LDU __ldg
 #endif
-#ifndef KITE_PF_INSTR
-#define KITE_PF_INSTR "prefetch.global.L2"
-#endif
 #ifndef KITE_ROLLOUT_BLOCK
 #define KITE_ROLLOUT_BLOCK 128
 #endif
@@ -212,14 +209,12 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
     for (int c = 0; c < 13; ++c) xs[c * ROLLOUT_BLOCK] = x[c];
 #endif
 
-    // Controls.  KITE_U_PER_STEP streams 24 B per state-step from HBM: the lines of step k + 3 are pulled into L2 by a
-    // register-free prefetch, and the (then short-latency) loads of step k + 1 are issued at the top of step k (below).
+    // Controls.  KITE_U_PER_STEP streams 24 B per state-step from HBM; the loads of step k + 1 are issued at the top of step k
+    // (below) and have a whole step (~4 us) to land, so nothing else is needed: the L2 prefetch two steps ahead that round 1
+    // used cost 1.4 % once the loads were a step ahead (78.88 -> 77.78 ms, profiles/r2w_sweep_nopf.log).
     // Loop state is kept small on purpose (the RHS leaves few spare registers): a 32-bit step counter and ONE running pointer
     // per stream instead of 64-bit index arithmetic per step.
     const int N = (int)a.N;                         // < 2^31 (checked by the host)
-    unsigned lane_id;
-    asm("mov.u32 %0, %%laneid;" : "=r"(lane_id));                // re-materialisable anywhere: nothing to keep alive across the loop
-    const bool pf_lane = (lane_id & 15) == 0;
     const long ustep = 3 * a.ld;
     const double* up = (UMODE == 1) ? a.u + i : a.u;            // per-trajectory stream / shared log / held control
     auto load_u = [&](int k, double (&uu)[3]) {
@@ -241,8 +236,8 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
     const double Qc[13] = {1e3, 1e2, 1e2, 1e2, 1e2, 1e2, 1e1, 1e1, 1e2, 1e2, 1e2, 1e2, 1e2};  // kite_identification_test.cpp:193
     const double* yp = a.y;
     int next_save = (int)a.save_every;
-    // Controls of step k + 1 are loaded at the TOP of step k and fly behind its arithmetic (three registers pairs; the lines
-    // were pulled into L2 two steps earlier).  Round 1 rejected this (61.5 % against 65.0 %) because the kernel spilled;
+    // Controls of step k + 1 are loaded at the TOP of step k and fly behind its arithmetic (three register pairs).
+    // Round 1 rejected this (61.5 % against 65.0 %) because the kernel spilled;
     // spill free (and still spill free at a 152-register cap) it is worth 1.5 %: 80.05 -> 78.85 ms (profiles/r2w_sweep_ureg.log).
     double un[3] = {0.0, 0.0, 0.0};
     if constexpr (UMODE == 1) { load_u(0, un); up += ustep; }
@@ -252,11 +247,6 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
             for (int c = 0; c < 3; ++c) u[c] = un[c];
             if (k + 1 < N) {
                 load_u(k + 1, un);
-                if (pf_lane && k + 3 < N) {                          // one prefetch per 128-byte line, two steps ahead of the load
-                    const double* pf = up + 2 * ustep;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) asm volatile(KITE_PF_INSTR " [%0];" :: "l"(pf + (long)c * a.ld));
-                }
                 up += ustep;
             }
         } else if constexpr (UMODE == 2) {           // shared log: every thread reads the same three words (L1 broadcast hits)
