@@ -77,3 +77,19 @@ def test_work_size_queries(lib):
     assert 8 <= big // per_warp <= 256 * 8 + (1 << 19) * 4 // per_warp + 1
     assert lib.kite_ekf_work_bytes(10) == 0          # EKF predict keeps the Jacobian in shared memory
     assert lib.kite_rk4_sens_work_bytes(0) == 0
+
+
+def test_every_kernel_is_spill_free(lib):
+    """north_star asks for zero register spills: the ptxas logs of the in-tree build (`-Xptxas -v`) must report 0 bytes of
+    stack, spill stores and spill loads for every kernel of the library, and the headline kernel must keep its 168 registers
+    (3 CTAs of 128 threads per SM)."""
+    from openkite_b200 import build as b
+    rows = b.resource_report()
+    assert len(rows) >= 40, "ptxas logs missing: run python -m openkite_b200.build --force"
+    bad = [(n, st, ss, sl) for n, regs, st, ss, sl in rows if ss or sl]
+    assert not bad, "kernels with register spills: %s" % bad
+    # a stack frame without spills is libm's large-argument path of sincos in the NMPC cost kernel; nothing else may have one
+    framed = [n for n, regs, st, ss, sl in rows if st and "k_colloc_cost" not in n]
+    assert not framed, "kernels with a stack frame: %s" % framed
+    head = [regs for n, regs, st, ss, sl in rows if "k_rk4_rolloutILi1ELb0ELb0" in n]
+    assert head and head[0] <= 168
