@@ -240,7 +240,7 @@ __device__ __forceinline__ void rollout_body(const RolloutArgs& a, double (&x)[1
     // Round 1 rejected this (61.5 % against 65.0 %) because the kernel spilled;
     // spill free (and still spill free at a 152-register cap) it is worth 1.5 %: 80.05 -> 78.85 ms (profiles/r2w_sweep_ureg.log).
     double un[3] = {0.0, 0.0, 0.0};
-    if constexpr (UMODE == 1) { load_u(0, un); up += ustep; }
+    if constexpr (UMODE == 1) { if (N > 0) load_u(0, un); up += ustep; }      // (N = 0 is legal: the control buffer may be empty)
     for (int k = 0; k < N; ++k) {
         if constexpr (UMODE == 1) {
 #pragma unroll

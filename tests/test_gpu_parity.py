@@ -233,6 +233,23 @@ def test_rollout_empty_and_single(eng, okb):
     assert out["xf"].shape == (13, 0)
 
 
+def test_rollout_zero_and_one_step(eng, okb, oracle):
+    """N = 0 returns the initial states untouched in every control mode (the per-step stream may be a one-row placeholder:
+    nothing of it is consumed); N = 1 is the single RK4 step -- the shortest horizon of the control-prefetch logic."""
+    B, h = 77, 1e-3
+    x0 = oracle.synth_x0(900, B)
+    uall = oracle.synth_controls(900, B, 2)                 # [B][2][3]
+    u_step = torch.from_numpy(np.ascontiguousarray(uall.transpose(1, 2, 0))).cuda()      # [2][3][B]
+    for mode, u in ((okb.U_CONST, soa(uall[:, 0, :])), (okb.U_PER_STEP, u_step[:1].contiguous()),
+                    (okb.U_SHARED, torch.from_numpy(uall[0].copy()).cuda())):
+        out = eng.rollout(soa(x0), u, 0, h, mode)
+        assert np.array_equal(aos(out["xf"]), x0), "N = 0, mode %d" % mode
+    out = eng.rollout(soa(x0), u_step[:1].contiguous(), 1, h, okb.U_PER_STEP)
+    assert_close(aos(out["xf"]), oracle.rollout(x0, uall[:, :1, :].copy(), 1, h, u_mode=1), RTOL, what="one step")
+    out = eng.rollout(soa(x0), u_step, 2, h, okb.U_PER_STEP)
+    assert_close(aos(out["xf"]), oracle.rollout(x0, uall, 2, h, u_mode=1), RTOL, what="two steps")
+
+
 def test_rollout_flags_nonfinite(eng, okb, oracle):
     x0 = oracle.synth_x0(0, 4)
     x0[2, 6:9] = 0.0                            # |r| = 0 -> division by zero in the tether term
