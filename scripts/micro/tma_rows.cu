@@ -15,7 +15,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Args { CUtensorMap in, out; long rounds; int F; unsigned box_bytes; int mode; };   // mode 1: load, 2: store, 3: both
+struct Args { CUtensorMap in, out; long rounds; int F; unsigned box_bytes; int mode; const double* lin_in; double* lin_out; };   // mode 1: load, 2: store, 3: both; lin_*: tiled layout [rounds][169][F], one contiguous 1-D bulk copy per box
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(256, 1) k_tma(const __grid_constant__ Args a, 
         if (lane == 0) {
             const unsigned bar = smem_u32(bars + (t & 1));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(a.box_bytes) : "memory");
+            if (a.lin_in)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(wb + (t & 1) * BOX)), "l"(a.lin_in + r * (long)(a.box_bytes / 8)), "r"(a.box_bytes), "r"(bar) : "memory");
+            else
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                          :: "r"(smem_u32(wb + (t & 1) * BOX)), "l"(reinterpret_cast<unsigned long long>(&a.in)), "r"((int)(r * a.F)), "r"(0), "r"(bar) : "memory");
         }
@@ -56,6 +60,10 @@ __global__ void __launch_bounds__(256, 1) k_tma(const __grid_constant__ Args a, 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
+                if (a.lin_out)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(a.lin_out + r * (long)(a.box_bytes / 8)), "r"(smem_u32(box)), "r"(a.box_bytes) : "memory");
+                else
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                              :: "l"(reinterpret_cast<unsigned long long>(&a.out)), "r"((int)(r * a.F)), "r"(0), "r"(smem_u32(box)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -85,7 +93,7 @@ int main(int argc, char** argv) {
         const int F = Fs[fi];
         for (int sw = 0; sw < 2; ++sw) {
             if (sw && F == 32) continue;
-            Args a; a.F = F; a.box_bytes = 169u * F * 8u; a.rounds = B / F;
+            Args a; a.F = F; a.box_bytes = 169u * F * 8u; a.rounds = B / F; a.lin_in = nullptr; a.lin_out = nullptr;
             const cuuint64_t dims[2] = {(cuuint64_t)B, 169};
             const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
             const cuuint32_t box[2] = {(cuuint32_t)F, 169};
@@ -115,6 +123,29 @@ int main(int argc, char** argv) {
                            F * 8, sw, W, mode == 1 ? "load " : mode == 2 ? "store" : "both ", best, B, bytes / best / 1e9,
                            best * 1e-3 * 1.965e9 / (169.0 * (B / F) / sms * ((mode & 1) + (mode >> 1))));
                 }
+            }
+        }
+    }
+    // tiled layout: the same bytes as [rounds][169][8]: one contiguous 10.8 KB bulk copy per box
+    {
+        Args a; a.F = 8; a.box_bytes = 169u * 8u * 8u; a.rounds = B / 8; a.lin_in = P; a.lin_out = Pn;
+        const size_t BOX = (a.box_bytes + 1023) / 1024 * 1024;
+        for (int W = 2; W <= 8; W += 2) {
+            const size_t smem = (size_t)W * 2 * BOX + 16 * W;
+            for (int mode = 1; mode <= 3; ++mode) {
+                a.mode = mode;
+                float best = 1e9f;
+                for (int rep = 0; rep < 4; ++rep) {
+                    cudaEventRecord(e0);
+                    k_tma<<<sms, W * 32, smem>>>(a, sink);
+                    cudaEventRecord(e1);
+                    CK(cudaEventSynchronize(e1));
+                    float ms; cudaEventElapsedTime(&ms, e0, e1);
+                    if (rep && ms < best) best = ms;
+                }
+                const double bytes = 169.0 * 8 * B * ((mode & 1) + (mode >> 1));
+                printf("tiled [B/8][169][8], 1-D bulk copies of %u B  warps/SM %d  %s  %.3f ms per %ld filters  %.2f TB/s\n",
+                       a.box_bytes, W, mode == 1 ? "load " : mode == 2 ? "store" : "both ", best, B, bytes / best / 1e9);
             }
         }
     }
