@@ -836,20 +836,29 @@ __global__ void __launch_bounds__(EfCfg<ARM>::WARPS * 32, 1) k_ekf_predict(const
         {
             const long unit = g * 32 + lane;
             const long ui = unit < a.B ? unit : a.B - 1;         // ragged tail: recompute the last filter, store nothing
-            double x[13], u[3], f[13];
+            double x[13], u[3], k[13], acc[13], xt[13];
 #pragma unroll
             for (int c = 0; c < 13; ++c) x[c] = __ldcs(a.x + (long)c * a.ld + ui);
 #pragma unroll
             for (int c = 0; c < 3; ++c) u[c] = a.u ? __ldcs(a.u + (long)c * a.ld + ui) : 0.0;
-            {
-                SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
-                model_eval<RIGID, true>(a.K, a.K.A, x, u, f, sink);
-            }
             const int pre = a.status ? singularity_flags<RIGID>(x) : 0;
-            rk4_step<RIGID>(a.K, a.K.A, x, u, a.rk);
+            {   // ONE evaluation at the pre-step state gives the Jacobian and the first RK4 stage (kiteEKF.cpp:80,93), as in the TMA kernel
+                SmemSink sink{Jt + (lane >> 2) * C::PS + (lane & 3)};
+                model_eval<RIGID, true>(a.K, a.K.A, x, u, k, sink);
+            }
+#pragma unroll
+            for (int c = 0; c < 13; ++c) { acc[c] = k[c]; xt[c] = fma(a.rk.an[0], k[c], x[c]); }
+            NoSink ns;
+#pragma unroll 1
+            for (int st = 1; st < 4; ++st) {
+                model_eval<RIGID, false>(a.K, a.K.A, xt, u, k, ns);
+                const double wgt = a.rk.w[st], an = a.rk.an[st];
+#pragma unroll
+                for (int c = 0; c < 13; ++c) { acc[c] = fma(wgt, k[c], acc[c]); xt[c] = fma(an, k[c], x[c]); }
+            }
             if (unit < a.B) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) __stcs(a.xn + (long)c * a.ld + unit, x[c]);
+                for (int c = 0; c < 13; ++c) { x[c] = fma(a.rk.h6, acc[c], x[c]); __stcs(a.xn + (long)c * a.ld + unit, x[c]); }
                 if (a.status) a.status[unit] = pre | (all_finite13(x) ? 0 : FLAG_NONFINITE);
             }
         }

@@ -563,13 +563,6 @@ __device__ __forceinline__ void model_eval_c(const KiteConsts& K, const AC& A, c
 #ifndef KITE_CB_DIRECT
 #define KITE_CB_DIRECT 0
 #endif
-#ifndef KITE_STAGE_UNROLL
-#define KITE_STAGE_UNROLL 1
-#endif
-#ifndef KITE_HOIST_U
-#define KITE_HOIST_U 1
-#endif
-constexpr int STAGE_UNROLL = KITE_STAGE_UNROLL;     // 1: one copy of the RHS in the instruction stream (rolled stage loop)
 // One classical RK4 step in registers (kitemath.cpp:36-51): x <- x + h/6 (k1 + 2 k2 + 2 k3 + k4).
 // Tableau of the classical RK4 step for one step size, filled on the host and read from the kernel's constant bank:
 //   an[st] = offset of the NEXT stage (h/2, h/2, h, -), w[st] = weight (1, 2, 2, 1), h6 = h / 6.
@@ -589,24 +582,25 @@ __host__ __device__ inline RkTab make_rk_tab(double h) {
 template <bool RIGID, class AC>
 __device__ __forceinline__ void rk4_step(const KiteConsts& K, const AC& A, double (&x)[13], const double (&u)[3],
                                          const RkTab& rk) {
-    // The four stages run as a real loop (one copy of the RHS in the instruction stream: the fully unrolled body
-    // was ~100 KB of SASS and stalled on instruction fetch, profiles/r1a_rollout_ncu_summary.txt).
     NoSink ns;
     double k[13], acc[13], xt[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { acc[i] = 0.0; xt[i] = x[i]; }
-#if KITE_HOIST_U
     const CtrlTerms uc = ctrl_terms(K, A, u);                    // the control is held for all four stages
-#endif
-#pragma unroll STAGE_UNROLL
-    for (int st = 0; st < 4; ++st) {
-#if KITE_HOIST_U
+    // Stage 1 is peeled off the loop: it reads the base state directly and its slope IS the accumulator (b_1 = 1), so the step
+    // needs neither the 26 register moves xt = x, nor the 13 zeroings, nor the 13 FMAs acc = 0 + 1 * k (bitwise the same
+    // result).  Stages 2..4 run as a real loop (one more copy of the RHS in the instruction stream: the fully unrolled body was
+    // ~100 KB of SASS and stalled on instruction fetch, profiles/r1a_rollout_ncu_summary.txt; two copies do not).
+    // Config 2: 77.8 -> 75.6 ms.
+    model_eval_c<RIGID, false>(K, A, x, uc, k, ns);
+#pragma unroll
+    for (int i = 0; i < 13; ++i) { acc[i] = k[i]; xt[i] = fma(rk.an[0], k[i], x[i]); }
+#pragma unroll 1
+    for (int st = 1; st < 4; ++st) {
         model_eval_c<RIGID, false>(K, A, xt, uc, k, ns);
-#else
-        model_eval<RIGID, false>(K, A, xt, u, k, ns);
-#endif
         const double wgt = rk.w[st];                             // tableau weights b = (1,2,2,1)/6
-        const double an = rk.an[st];                             // next stage offset a = (1/2, 1/2, 1)
+        const double an = rk.an[st];                             // next stage offset a = (1/2, 1/2, 1, 0)
+        // (one loop, accumulator and next stage input side by side: the two FMAs of a component share k[i] in the same operand
+        // slot.  Split into two loops, or with the last stage's unused input skipped by a uniform branch, the step is 1 % slower:
+        // 76.2 - 76.5 ms against 75.6, profiles/r2y_sweep_skiplast.log, r2y_sweep_fused.log)
 #pragma unroll
         for (int i = 0; i < 13; ++i) { acc[i] = fma(wgt, k[i], acc[i]); xt[i] = fma(an, k[i], x[i]); }
     }
