@@ -1152,7 +1152,11 @@ struct EkfUpdArgs {
     const double* V;         // device [49]
     int32_t* status;         // [ld] per-filter flag (non-finite updated state: singular innovation covariance) or null
 };
+#ifndef KITE_EKFU_COLS
+#define KITE_EKFU_COLS 2
+#endif
 constexpr int EKFU_BLOCK = 128;
+constexpr int EKFU_COLS = KITE_EKFU_COLS;       // covariance columns per pass of the update
 constexpr int EKFU_KUNROLL = 4;      // rows of K in flight: 28 loads instead of 7 between dependent DRAM round trips (0.88 -> 0.81 ms)
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_constant__ EkfUpdArgs a) {
@@ -1212,44 +1216,45 @@ __global__ void __launch_bounds__(EKFU_BLOCK, 2) k_ekf_update(const __grid_const
     // P[:, c] <- P[:, c] - K (H P)[:, c], TWO columns per pass: every gain entry read from shared memory serves both, the next
     // pair's 26 loads fly behind this pair's FMAs, and the pair after that is pulled into L2 (register free).  (H P)[:, c] is
     // rows 6..12 of column c itself: no separate loads.  Column 13 does not exist: the last pass handles column 12 alone.
-    double pv[2][13], pq[2][13];
+    constexpr int NC = EKFU_COLS;
+    double pv[NC][13], pq[NC][13];
 #pragma unroll
-    for (int r = 0; r < 13; ++r) { pv[0][r] = P[(long)(r * 13) * ld]; pv[1][r] = P[(long)(r * 13 + 1) * ld]; }
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int r = 0; r < 13; ++r) pv[j][r] = P[(long)(r * 13 + j) * ld];
 #pragma unroll 1
-    for (int c = 0; c < 13; c += 2) {
-        if (c + 4 < 13 && (threadIdx.x & 15) == 0) {
+    for (int c = 0; c < 13; c += NC) {
+        if ((threadIdx.x & 15) == 0) {
 #pragma unroll
-            for (int r = 0; r < 13; ++r) {
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(P + (long)(r * 13 + c + 4) * ld));
-                if (c + 5 < 13) asm volatile("prefetch.global.L2 [%0];" :: "l"(P + (long)(r * 13 + c + 5) * ld));
-            }
-        }
-        if (c + 2 < 13) {
+            for (int j = 0; j < NC; ++j)
+                if (c + 2 * NC + j < 13) {
 #pragma unroll
-            for (int r = 0; r < 13; ++r) {
-                pq[0][r] = P[(long)(r * 13 + c + 2) * ld];
-                pq[1][r] = (c + 3 < 13) ? P[(long)(r * 13 + c + 3) * ld] : 0.0;
-            }
+                    for (int r = 0; r < 13; ++r) asm volatile("prefetch.global.L2 [%0];" :: "l"(P + (long)(r * 13 + c + 2 * NC + j) * ld));
+                }
         }
-        double o0[13], o1[13];
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+#pragma unroll
+            for (int r = 0; r < 13; ++r) pq[j][r] = (c + NC + j < 13) ? P[(long)(r * 13 + c + NC + j) * ld] : 0.0;
 #pragma unroll
         for (int r = 0; r < 13; ++r) {
-            double v0 = pv[0][r], v1 = pv[1][r];
+            double v[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] = pv[j][r];
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const double kk = Ks[(r * 7 + k) * EKFU_BLOCK];
-                v0 = fma(-kk, pv[0][6 + k], v0);
-                v1 = fma(-kk, pv[1][6 + k], v1);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) v[j] = fma(-kk, pv[j][6 + k], v[j]);
             }
-            o0[r] = v0; o1[r] = v1;
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+                if (c + j < 13) P[(long)(r * 13 + c + j) * ld] = v[j];
         }
 #pragma unroll
-        for (int r = 0; r < 13; ++r) {
-            P[(long)(r * 13 + c) * ld] = o0[r];
-            if (c + 1 < 13) P[(long)(r * 13 + c + 1) * ld] = o1[r];
-        }
+        for (int j = 0; j < NC; ++j)
 #pragma unroll
-        for (int r = 0; r < 13; ++r) { pv[0][r] = pq[0][r]; pv[1][r] = pq[1][r]; }
+            for (int r = 0; r < 13; ++r) pv[j][r] = pq[j][r];
     }
 }
 
